@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — LaneGCN forward scenes/sec (batch 128) on 1/2/4/8 B200 + LaneConv gather HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 128] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): one global batch of 128 synthetic Argoverse-shaped scenes ("argo-1.5k":
+1,512 lane nodes, 20 actors, 18.7k edges per scene), cut into contiguous scene shards across the N ranks
+(strong scaling: total work fixed).  A step = one full Net forward of the rank's shard + the final NCCL
+gather of cls/reg.  ``value`` times the step from the staged (HBM-resident) batch with CUDA events; ``e2e``
+times Net.forward(collated CPU dict) -> cls/reg back on the host (pinned staging, H2D and D2H inside).
+``roofline`` is the LaneConv gather kernel timed by CUDA events inside the same timed steps.
+``cpu_baseline`` / ``--impl reference`` time the CPU oracle port of the reference forward on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LaneGCN fwd scenes/sec (batch 128)"
+PRESET = "argo-1.5k"
+CPU_SAMPLE_SCENES = 32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_forward_rate(steps: int, warmup: int, n_scenes: int = CPU_SAMPLE_SCENES):
+    """scenes/s of the reference forward restated on CPU (oracle/lanegcn_oracle.py: same torch ops, same
+    order as lanegcn.py:127-151), all host threads, on a bounded sample of the workload."""
+    import torch
+
+    from lanegcn_b200 import synth
+    from oracle import lanegcn_oracle as O
+
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_shapes.json")))
+    sd = synth.seeded_state_dict(shapes, 0)
+    data = synth.collate(synth.make_scenes(n_scenes, PRESET, seed0=0))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.net_forward(sd, data)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return n_scenes / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    v, ms, cores = cpu_forward_rate(steps, warmup)
+    sample = (f"{CPU_SAMPLE_SCENES} of the {args.batch} scenes per step (same preset and seeds), "
+              f"{warmup} warm-up + {steps} timed forwards, oracle port of lanegcn.py:127-151 on CPU fp32")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "scenes/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"LaneGCN forward, batch {args.batch} synthetic {PRESET} scenes (configs[2])",
+                   "note": "CPU arm processes a bounded sample per step"},
+        "cpu_baseline": {"value": round(v, 3), "unit": "scenes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            mx.append(int(f[1]))
+            reasons |= {n for n, x in zip(names, f[2:6]) if x.lower().startswith("active")}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from lanegcn_b200 import _C, build, shard, synth
+    from lanegcn_b200 import lanegcn as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(_C.LIB_PATH):
+        if rank == 0:
+            build.build()
+        if world > 1:
+            dist.barrier()
+    lib = _C.lib()
+
+    # ---- workload: global batch, this rank's contiguous shard
+    B = args.batch
+    costs = [1512] * B  # every argo-1.5k scene has the same node count: equal scene counts per rank
+    mine = shard.partition(costs, world)[rank]
+    scenes = [synth.make_scene(i, PRESET) for i in mine]
+    data = synth.collate(scenes)
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_shapes.json")))
+    net = L.Net(L.config)
+    net.load_state_dict(synth.seeded_state_dict(shapes, 0))
+    net = net.to(dev).eval()
+
+    def step_device(staged):
+        out = net.forward_device(staged)
+        return shard.gather_outputs(out) if world > 1 else out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    staged = net.stage(data)
+    for _ in range(max(args.warmup, 3)):
+        step_device(staged)
+    sync_all()
+
+    # ---- timed: K steps from HBM-resident inputs, CUDA events per step, L2 flushed between steps
+    n_nodes = sum(int(s["graph"]["num_nodes"]) for s in scenes)
+    n_edges = sum(sum(len(e["u"]) for e in s["graph"]["pre"] + s["graph"]["suc"])
+                  + len(s["graph"]["left"]["u"]) + len(s["graph"]["right"]["u"]) for s in scenes)
+    clocks = Clocks(local) if rank == 0 else None
+    lib.lgcn_prof_enable(1)
+    launches0 = lib.lgcn_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step_device(staged)
+        b.record()
+    sync_all()
+    launches = lib.lgcn_launch_count() - launches0
+    lib.lgcn_prof_enable(0)
+    ms_kind = (ctypes.c_double * 4)()
+    n_kind = (ctypes.c_int64 * 4)()
+    _C.check(lib.lgcn_prof_collect(ms_kind, n_kind), "prof_collect")
+    clk = clocks.stop() if clocks else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t.item()) / args.steps
+    value = B / (ms_per_step / 1e3)
+
+    # ---- end to end: collated CPU dict -> outputs on the host, wall clock, max over ranks
+    def step_e2e():
+        out = net(data)
+        if world > 1:
+            out = shard.gather_outputs(out)
+        return torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
+
+    for _ in range(3):
+        cls, reg = step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cls, reg = step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    hb = torch.tensor([float(net.stage(data).h2d_bytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+    e2e_ms = float(te.item())
+    d2h = int(cls.numel() * 4 + reg.numel() * 4) * (world if world > 1 else 1)  # every rank reads the gathered result
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant HBM-bound kernel: the LaneConv gather (rank 0's shard)
+    peak, peak_src = peaks()
+    gather_bytes = 4 * 128 * (n_edges + 2 * n_nodes) + 4 * n_edges + 4 * (n_nodes + 1)
+    gather_ms = ms_kind[1] / max(1, n_kind[1])
+    achieved = gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gather_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("n_nodes") == n_nodes:
+            traffic = tj.get("dram_bytes_per_launch")
+    step_kernel_ms = {k: round(ms_kind[i] / args.steps, 4) for i, k in enumerate(["wide_gemm", "gather", "ctr2", "att"])}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, cores = cpu_forward_rate(3, 1)
+        cpu = {"value": round(v, 3), "unit": "scenes/s", "cores": cores, "kind": "port",
+               "sample": f"{CPU_SAMPLE_SCENES} of the {B} scenes (same preset/seeds), 1 warm-up + 3 timed forwards "
+                         f"of the oracle port (oracle/lanegcn_oracle.py) on the host CPU, fp32"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"LaneGCN forward, batch {B} synthetic {PRESET} scenes (BASELINE configs[2]), "
+                               f"scene-sharded over {world} GPU(s)",
+                   "global_batch": B, "scenes_per_gpu": len(scenes), "nodes_per_gpu": n_nodes,
+                   "edges_per_gpu": n_edges, "gemm_engine": ["simt-fp32", "tcgen05-3xtf32"][lib.lgcn_get_gemm_engine()],
+                   "l2": "256 MiB flush between timed steps; per-step working set (Y alone "
+                         f"{n_nodes * 1920 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2",
+                   "kernel_ms_per_step": step_kernel_ms},
+        "e2e": {"value": round(B / (e2e_ms / 1e3), 2), "unit": "scenes/s", "ms_per_step": round(e2e_ms, 4),
+                "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(lt.item()),
+        "roofline": {"kernel": "k_gather_gn_relu (LaneConv gather + GN + ReLU)", "bound": "hbm",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": round(gather_ms, 5),
+                     "launches_timed": int(n_kind[1])},
+        "clocks": clk,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:  # convenience: re-launch ourselves under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+/*
+ * lgcn.h — C ABI of liblgcn_b200.so: the LaneGCN forward graph path on B200 (sm_100a).
+ *
+ * The reference (leepaul009/LaneGCN-1) has no plugin/FFI surface: its boundary is the Python module API of
+ * lanegcn.py.  Each entry point below replaces the body of one reference function / loop; the reference-side
+ * binding is a ctypes stub, the in-repo one is lanegcn-1_b200/_C.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless its name starts with h_.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises unless
+ *     the comment says so.  The library never allocates, frees or retains caller memory: outputs and
+ *     workspaces are caller-provided (sizes from the *_workspace_bytes helpers).
+ *   - return 0 on success, <0 on error; lgcn_last_error() gives the thread-local message.
+ *   - feature matrices are row-major fp32 with 128 channels (config n_map = n_actor = 128).
+ *   - nn.Linear weights are [out, in] row-major (y = x * W^T), as in the reference state_dict.
+ */
+#ifndef LGCN_H_
+#define LGCN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGCN_C 128            /* channels */
+#define LGCN_MAX_KEYS 16      /* edge sets per LaneConv block (reference: 14) */
+
+/* epilogue flags of lgcn_linear128 (order of application: GN -> RELU1 -> +RES -> RELU2) */
+#define LGCN_EPI_GN    1      /* GroupNorm(1 group) over the 128 outputs: layers.py:72 */
+#define LGCN_EPI_RELU1 2      /* ReLU right after the norm: layers.py:84-85 (act=True) */
+#define LGCN_EPI_RES   4      /* += res[m,:] : lanegcn.py:360, 707 */
+#define LGCN_EPI_RELU2 8      /* final ReLU: lanegcn.py:361, 708 */
+
+int lgcn_version(void);
+const char* lgcn_last_error(void);
+/* which GEMM engine the library will use on this process: 0 = fp32 SIMT, 1 = tcgen05 3xTF32.
+ * set_gemm_engine returns the previous value. */
+int lgcn_get_gemm_engine(void);
+int lgcn_set_gemm_engine(int engine);
+
+/* number of CUDA kernels this library has launched in this process (all entry points) */
+int64_t lgcn_launch_count(void);
+/* Per-kernel timing for the benchmark: while enabled, lgcn_laneconv_stack / lgcn_att_forward bracket their
+ * launches with CUDA events on the launching stream.  lgcn_prof_collect SYNCHRONISES on those events, returns
+ * summed milliseconds and launch counts per kind (0 wide projection GEMM, 1 LaneConv gather, 2 ctr2 linear,
+ * 3 whole Att layer; arrays of 4) and resets.  lgcn_prof_enable returns the previous state. */
+int lgcn_prof_enable(int on);
+int lgcn_prof_collect(double* h_ms_by_kind, int64_t* h_launches_by_kind);
+
+/* ------------------------------------------------------------------ graph batching
+ * replaces utils.to_long (utils.py:88-96) + the offset/cat loops of graph_gather (lanegcn.py:191-208).
+ * `local` holds S segments of scene-local indices (idx_bytes = 2, 4 or 8: int16/int32/int64) laid out
+ * back to back in output order; seg_start[S+1] are element offsets, seg_add[S] the node offset of the
+ * scene each segment belongs to.  out[i] = (int64) local[i] + seg_add[seg(i)].                           */
+int lgcn_offset_indices(const void* local, int idx_bytes, const int64_t* seg_start, const int64_t* seg_add,
+                        int n_segments, int64_t total, int64_t* out, void* stream);
+
+/* node-side batching helper: meta[n] = (turn[n,0], turn[n,1], control[n], intersect[n])
+ * (the cat at lanegcn.py:387-394, done once per batch).                                                  */
+int lgcn_pack_meta(const float* turn, const float* control, const float* intersect, float* meta, int64_t n,
+                   void* stream);
+
+/* Destination-sorted merged CSR of the K edge sets of one LaneConv block (accumulation order of
+ * lanegcn.py:333-354: key order as given, then edge-list order — a STABLE sort by destination u).
+ *   h_u[k], h_v[k] : device pointers to int64 u_k (destination) / v_k (source), h_len[k] their lengths
+ *   rowptr int32[n_nodes+1];  col int32[E] with col = v*(K+1) + (k+1)  (block index into Y[n, (K+1)*128])
+ * workspace: lgcn_csr_workspace_bytes(n_nodes, E).  Indices out of [0,n_nodes) are an error reported
+ * through *err_flag (device int32, set non-zero) — checked by the caller when it next synchronises.       */
+int64_t lgcn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len, int n_keys,
+                   int64_t n_nodes, int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag,
+                   void* stream);
+
+/* ------------------------------------------------------------------ dense pieces
+ * out[m, ob*128 + c] (row stride ldo) for ob in [0, n_out_blocks):
+ *     acc = sum_s  A_s[ idx_s ? idx_s[m] : m , 0:128 ] . W[ob*128 + c, s*128 : (s+1)*128]
+ *         + sum_j  xs[m, j] * W[ob*128 + c, n_src*128 + j]          (j < ks <= 4, optional)
+ *     then the epilogue flags (only valid when n_out_blocks == 1).
+ * W is [n_out_blocks*128, n_src*128 + ks] row-major.  n_src in 1..3.  idx_s are int32 row gathers.
+ * Replaces every bias-free nn.Linear / layers.Linear on the path:
+ *   fuse.{ctr,preS,sucS,left,right} (lanegcn.py:332-354, as ONE call with n_out_blocks = 15),
+ *   fuse.ctr2 (:359-361), MapNet input.2/seg.2 (:325-327), A2M.meta (:395, ks = 4),
+ *   Att.dist.2 / query / ctx.0 (3 sources, no materialised cat) / ctx.1 / agt / linear (:693-708).       */
+int lgcn_linear128(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1,
+                   const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks, const float* W,
+                   int n_out_blocks, const float* gamma, const float* beta, const float* res, int flags,
+                   float* out, int64_t ldo, int64_t m, void* stream);
+
+/* h[m,:] = relu(W1[128,2] . x[m] + b1), x[m] = p[ip ? ip[m] : m] - (q ? q[iq ? iq[m] : m] : 0)
+ * The nn.Linear(2,128)+ReLU heads of MapNet.input/seg (lanegcn.py:277-286) and Att.dist (:644-648, with
+ * x = agt_ctrs[hi] - ctx_ctrs[wi], :693).                                                                */
+int lgcn_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
+                 const float* b1, float* h, int64_t m, void* stream);
+
+/* LaneConv gather-reduce with fused GroupNorm(1)+ReLU (lanegcn.py:333-357 after the wide projection):
+ *   t = Y[n, 0:128];  for e in rowptr[n]..rowptr[n+1]: t += Y_blocks[col[e]];  out[n] = relu(GN(t))
+ * Y is [n_nodes, n_blocks*128]; Y_blocks[b] = Y + b*128 floats.  Fixed summation order => deterministic. */
+int lgcn_laneconv_gather_gn_relu(const float* Y, int n_blocks, const int32_t* rowptr, const int32_t* col,
+                                 const float* gamma, const float* beta, float* out, int64_t n_nodes,
+                                 void* stream);
+
+/* Att scatter (lanegcn.py:702-705): out[r] = relu(GN(a[r] + sum_{p in rowptr[r]..rowptr[r+1]} c[p])).
+ * Pairs are destination-sorted already (hi ascending), so the segments are contiguous rows of c.         */
+int lgcn_segsum_gn_relu(const float* a, const float* c, const int32_t* rowptr, const float* gamma,
+                        const float* beta, float* out, int64_t n_rows, void* stream);
+
+/* ------------------------------------------------------------------ Att pair list (lanegcn.py:672-689)
+ * Scenes b = 0..B-1 own agent rows agt_off[b]..agt_off[b+1] and context rows ctx_off[b]..ctx_off[b+1]
+ * (int32[B+1], device).  A pair (i,j) of the same scene exists iff sqrt(dx*dx + dy*dy) <= th, evaluated in
+ * fp32 with separately rounded sub / mul / add / sqrt (no FMA contraction) like the torch ops it replaces.
+ * Step 1 (count): per-agent counts -> rowptr int32[n_agt+1] (exclusive scan; rowptr[n_agt] = P) and the
+ *                 reference's empty-scene offset quirk resolved into per-scene output
+ *                 offsets.  *h_total (host int64, may be NULL) receives P — passing it SYNCHRONISES.
+ * Step 2 (fill):  hi/wi in row-major order.  hi32/wi32/hi64/wi64 may each be NULL.
+ * keep_quirk != 0 reproduces the reference (scenes after an empty scene are shifted down).
+ * rowptr is indexed by OUTPUT destination row (the value of hi), so it feeds lgcn_segsum_gn_relu as is. */
+int64_t lgcn_pairs_workspace_bytes(int64_t n_agt, int n_scenes);
+int lgcn_pairs_count(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off,
+                     const int32_t* ctx_off, int n_scenes, int64_t n_agt, float th, int keep_quirk,
+                     int32_t* rowptr, void* workspace, int64_t* h_total, void* stream);
+int lgcn_pairs_fill(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off,
+                    const int32_t* ctx_off, int n_scenes, int64_t n_agt, float th, const void* workspace,
+                    int32_t* hi32, int32_t* wi32, int64_t* hi64, int64_t* wi64, void* stream);
+
+/* ------------------------------------------------------------------ fused sequences (one call per module)
+ * LaneConv stack: the 4-block loop of MapNet.forward (lanegcn.py:331-362) == M2M.forward (:448-479).
+ * wpack: per block, contiguous fp32
+ *     Wcat[(K+1)*128,128] (rows: ctr, then the K keys in accumulation order) | Wctr2[128,128]
+ *     | norm.weight[128] | norm.bias[128] | ctr2.norm.weight[128] | ctr2.norm.bias[128]
+ * feat is updated in place ([n_nodes,128]).  workspace: lgcn_laneconv_workspace_bytes(n_nodes, K).       */
+int64_t lgcn_laneconv_wpack_floats(int n_keys);
+int64_t lgcn_laneconv_workspace_bytes(int64_t n_nodes, int n_keys);
+int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int32_t* col, int n_keys, int n_blocks,
+                        const float* wpack, int64_t n_nodes, void* workspace, void* stream);
+
+/* One Att layer (lanegcn.py:662-710) on a prebuilt pair list.  wpack, contiguous fp32:
+ *   dist.0.weight[128,2] | dist.0.bias[128] | dist.2.linear.weight[128,128] | dist.2.norm.{weight,bias}
+ *   | query.linear.weight[128,128] | query.norm.{w,b} | ctx.0.linear.weight[128,384] | ctx.0.norm.{w,b}
+ *   | ctx.1.weight[128,128] | agt.weight[128,128] | norm.{w,b} | linear.linear.weight[128,128]
+ *   | linear.norm.{w,b}
+ * agts_in/agts_out [n_agt,128] (may alias), ctx [n_ctx,128]; n_pairs may be 0 only together with
+ * n_ctx == 0 (the reference's early-out path :664-670, which skips self.norm).                          */
+int64_t lgcn_att_wpack_floats(void);
+int64_t lgcn_att_workspace_bytes(int64_t n_agt, int64_t n_pairs);
+int lgcn_att_forward(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs,
+                     const float* ctx_ctrs, const int32_t* hi, const int32_t* wi, const int32_t* rowptr,
+                     int64_t n_agt, int64_t n_ctx, int64_t n_pairs, const float* wpack, void* workspace,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCN_H_ */

@@ -1,0 +1,261 @@
+// api.cu — C-ABI glue: error reporting, engine selection, lgcn_linear128 argument checking, and the two
+// fused per-module sequences (LaneConv stack, Att layer) that keep the host at one call per module.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void lgcn_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t lgcn_launch_count(void) { return g_launches.load(); }
+
+// ---- per-kernel timing: event pairs on the launching stream, summed per kind by lgcn_prof_collect
+struct ProfEv { cudaEvent_t a, b; int kind; };
+static std::vector<ProfEv> g_prof_pool;
+static size_t g_prof_used = 0;
+static bool g_prof_on = false;
+LgcnProfScope::LgcnProfScope(int kind, cudaStream_t s) : slot(-1), st(s) {
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof_pool.size()) {
+    ProfEv e;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    g_prof_pool.push_back(e);
+  }
+  slot = (int)g_prof_used++;
+  g_prof_pool[slot].kind = kind;
+  cudaEventRecord(g_prof_pool[slot].a, st);
+}
+LgcnProfScope::~LgcnProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof_pool[slot].b, st);
+}
+extern "C" int lgcn_prof_enable(int on) {
+  const int prev = g_prof_on;
+  g_prof_on = on != 0;
+  return prev;
+}
+extern "C" int lgcn_prof_collect(double* ms_by_kind, int64_t* launches_by_kind) {
+  for (int k = 0; k < LGCN_PROF_KINDS; ++k) {
+    ms_by_kind[k] = 0.0;
+    launches_by_kind[k] = 0;
+  }
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float ms = 0.f;
+    LGCN_CUDA_OK(cudaEventSynchronize(g_prof_pool[i].b));
+    LGCN_CUDA_OK(cudaEventElapsedTime(&ms, g_prof_pool[i].a, g_prof_pool[i].b));
+    ms_by_kind[g_prof_pool[i].kind] += ms;
+    launches_by_kind[g_prof_pool[i].kind] += 1;
+  }
+  g_prof_used = 0;
+  return 0;
+}
+static int g_engine = -1;  // -1: not decided yet
+
+void lgcn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* lgcn_last_error(void) { return g_err; }
+extern "C" int lgcn_version(void) { return 100; }
+
+extern "C" int lgcn_get_gemm_engine(void) {
+  if (g_engine < 0) {
+    const char* e = getenv("LGCN_GEMM_ENGINE");
+    g_engine = (e && strcmp(e, "simt") == 0) ? 0 : LGCN_DEFAULT_ENGINE;
+  }
+  return g_engine;
+}
+extern "C" int lgcn_set_gemm_engine(int engine) {
+  const int prev = lgcn_get_gemm_engine();
+  g_engine = (engine && LGCN_HAVE_TC) ? 1 : 0;  // engine 1 only exists when gemm_tc.cu was built in
+  return prev;
+}
+
+int lgcn_launch_linear(const LinearArgs& a, cudaStream_t st) {
+#if LGCN_HAVE_TC
+  if (lgcn_get_gemm_engine() == 1) return lgcn_launch_linear_tc(a, st);
+#endif
+  return lgcn_launch_linear_simt(a, st);
+}
+
+static int check_linear(const LinearArgs& a) {
+  LGCN_CHECK_ARG(a.n_src >= 1 && a.n_src <= 3, "linear128: n_src %d not in 1..3", a.n_src);
+  LGCN_CHECK_ARG(a.ks == 0 || a.ks == 4, "linear128: ks %d (only 0 or 4: W rows must stay 16-byte aligned)", a.ks);
+  LGCN_CHECK_ARG(a.ks == 0 || a.xs, "linear128: ks > 0 without xs");
+  LGCN_CHECK_ARG(a.n_out_blocks >= 1, "linear128: n_out_blocks %d", a.n_out_blocks);
+  LGCN_CHECK_ARG(a.flags == 0 || a.n_out_blocks == 1, "linear128: epilogue flags need n_out_blocks == 1");
+  LGCN_CHECK_ARG(!(a.flags & LGCN_EPI_GN) || (a.gamma && a.beta), "linear128: GN without gamma/beta");
+  LGCN_CHECK_ARG(!(a.flags & LGCN_EPI_RES) || a.res, "linear128: RES without res");
+  LGCN_CHECK_ARG(a.ldo >= (int64_t)a.n_out_blocks * LGCN_C && a.ldo % 4 == 0, "linear128: bad ldo %lld", (long long)a.ldo);
+  for (int s = 0; s < a.n_src; ++s) LGCN_CHECK_ARG(a.a[s], "linear128: source %d is NULL", s);
+  LGCN_CHECK_ARG(a.W && a.out, "linear128: NULL W/out");
+  return 0;
+}
+
+extern "C" int lgcn_linear128(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1,
+                              const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks,
+                              const float* W, int n_out_blocks, const float* gamma, const float* beta,
+                              const float* res, int flags, float* out, int64_t ldo, int64_t m, void* stream) {
+  LinearArgs a;
+  a.a[0] = a0; a.a[1] = a1; a.a[2] = a2;
+  a.idx[0] = idx0; a.idx[1] = idx1; a.idx[2] = idx2;
+  a.n_src = n_src; a.xs = xs; a.ks = ks; a.W = W; a.n_out_blocks = n_out_blocks;
+  a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = ldo; a.m = m;
+  if (check_linear(a)) return -1;
+  return lgcn_launch_linear(a, (cudaStream_t)stream);
+}
+
+static LinearArgs lin1(const float* x, const int32_t* idx, const float* W, const float* gamma, const float* beta,
+                       const float* res, int flags, float* out, int64_t m) {
+  LinearArgs a;
+  memset(&a, 0, sizeof(a));
+  a.a[0] = x; a.idx[0] = idx; a.n_src = 1; a.W = W; a.n_out_blocks = 1;
+  a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = LGCN_C; a.m = m;
+  return a;
+}
+
+// ------------------------------------------------------------------ LaneConv stack
+#define CC ((int64_t)LGCN_C * LGCN_C)
+
+extern "C" int64_t lgcn_laneconv_wpack_floats(int n_keys) { return (int64_t)(n_keys + 1) * CC + CC + 4 * LGCN_C; }
+
+extern "C" int64_t lgcn_laneconv_workspace_bytes(int64_t n_nodes, int n_keys) {
+  return lgcn_align_up(n_nodes * (int64_t)(n_keys + 1) * LGCN_C * 4, 1024) + lgcn_align_up(n_nodes * LGCN_C * 4, 1024) + 1024;
+}
+
+extern "C" int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int32_t* col, int n_keys,
+                                   int n_blocks, const float* wpack, int64_t n_nodes, void* workspace,
+                                   void* stream) {
+  LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "laneconv_stack: n_keys %d", n_keys);
+  LGCN_CHECK_ARG(feat && rowptr && wpack && workspace, "laneconv_stack: NULL argument");
+  if (n_nodes <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = n_keys + 1;
+  float* Y = (float*)workspace;
+  float* h = (float*)((char*)workspace + lgcn_align_up(n_nodes * (int64_t)nb * LGCN_C * 4, 1024));
+  for (int i = 0; i < n_blocks; ++i) {
+    const float* w = wpack + (int64_t)i * lgcn_laneconv_wpack_floats(n_keys);
+    const float* wctr2 = w + (int64_t)nb * CC;
+    const float* gn_g = wctr2 + CC;
+    const float* gn_b = gn_g + LGCN_C;
+    const float* c2_g = gn_b + LGCN_C;
+    const float* c2_b = c2_g + LGCN_C;
+    // (1) all nb projections of every node in one wide GEMM: Y[n, k*128:(k+1)*128] = feat[n] . W_k^T
+    LinearArgs wide = lin1(feat, nullptr, w, nullptr, nullptr, nullptr, 0, Y, n_nodes);
+    wide.n_out_blocks = nb;
+    wide.ldo = (int64_t)nb * LGCN_C;
+    {
+      LgcnProfScope ps(LGCN_PROF_WIDE, st);
+      if (int rc = lgcn_launch_linear(wide, st)) return rc;
+    }
+    // (2) temp = ctr + sum over destination-sorted edges; h = relu(GN(temp))
+    {
+      LgcnProfScope ps(LGCN_PROF_GATHER, st);
+      if (int rc = lgcn_laneconv_gather_gn_relu(Y, nb, rowptr, col, gn_g, gn_b, h, n_nodes, stream)) return rc;
+    }
+    // (3) feat = relu(GN(h . Wctr2^T) + feat)     (res == current feat; written in place)
+    LinearArgs c2 = lin1(h, nullptr, wctr2, c2_g, c2_b, feat, LGCN_EPI_GN | LGCN_EPI_RES | LGCN_EPI_RELU2, feat, n_nodes);
+    {
+      LgcnProfScope ps(LGCN_PROF_CTR2, st);
+      if (int rc = lgcn_launch_linear(c2, st)) return rc;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ Att layer
+struct AttW {
+  const float *d0w, *d0b, *d2w, *d2g, *d2b, *qw, *qg, *qb, *c0w, *c0g, *c0b, *c1w, *aw, *ng, *nb, *lw, *lg, *lb;
+};
+static AttW att_unpack(const float* p) {
+  AttW w;
+  w.d0w = p; p += 2 * LGCN_C;
+  w.d0b = p; p += LGCN_C;
+  w.d2w = p; p += CC;
+  w.d2g = p; p += LGCN_C;
+  w.d2b = p; p += LGCN_C;
+  w.qw = p; p += CC;
+  w.qg = p; p += LGCN_C;
+  w.qb = p; p += LGCN_C;
+  w.c0w = p; p += 3 * CC;
+  w.c0g = p; p += LGCN_C;
+  w.c0b = p; p += LGCN_C;
+  w.c1w = p; p += CC;
+  w.aw = p; p += CC;
+  w.ng = p; p += LGCN_C;
+  w.nb = p; p += LGCN_C;
+  w.lw = p; p += CC;
+  w.lg = p; p += LGCN_C;
+  w.lb = p; p += LGCN_C;
+  return w;
+}
+extern "C" int64_t lgcn_att_wpack_floats(void) { return 2 * LGCN_C + LGCN_C + 8 * CC + 10 * LGCN_C; }
+
+extern "C" int64_t lgcn_att_workspace_bytes(int64_t n_agt, int64_t n_pairs) {
+  return 3 * lgcn_align_up(n_pairs * LGCN_C * 4, 1024) + 2 * lgcn_align_up(n_agt * LGCN_C * 4, 1024) + 1024;
+}
+
+extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs,
+                                const float* ctx_ctrs, const int32_t* hi, const int32_t* wi,
+                                const int32_t* rowptr, int64_t n_agt, int64_t n_ctx, int64_t n_pairs,
+                                const float* wpack, void* workspace, void* stream) {
+  LGCN_CHECK_ARG(agts_in && agts_out && wpack && workspace, "att_forward: NULL argument");
+  if (n_agt <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  LgcnProfScope ps(LGCN_PROF_ATT, st);
+  const AttW w = att_unpack(wpack);
+  const int64_t pb = lgcn_align_up(n_pairs * LGCN_C * 4, 1024), ab = lgcn_align_up(n_agt * LGCN_C * 4, 1024);
+  float* P0 = (float*)workspace;
+  float* P1 = (float*)((char*)workspace + pb);
+  float* P2 = (float*)((char*)workspace + 2 * pb);
+  float* A0 = (float*)((char*)workspace + 3 * pb);
+  float* A1 = (float*)((char*)workspace + 3 * pb + ab);
+  const int kLin = LGCN_EPI_GN | LGCN_EPI_RES | LGCN_EPI_RELU2;
+  if (n_ctx == 0) {  // lanegcn.py:664-670 — no self.norm on this path
+    LinearArgs a = lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, LGCN_EPI_RELU1, A0, n_agt);
+    if (int rc = lgcn_launch_linear(a, st)) return rc;
+    LinearArgs l = lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt);
+    return lgcn_launch_linear(l, st);
+  }
+  LGCN_CHECK_ARG(n_pairs > 0, "att_forward: no agent/context pair within the distance threshold in any scene "
+                              "(the reference raises at lanegcn.py:688: torch.cat of an empty list)");
+  LGCN_CHECK_ARG(ctx && agt_ctrs && ctx_ctrs && hi && wi && rowptr, "att_forward: NULL argument");
+  // dist = relu(GN(L(relu(L2(agt_ctrs[hi] - ctx_ctrs[wi])))))                      lanegcn.py:693-694
+  if (int rc = lgcn_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, stream)) return rc;
+  LinearArgs d2 = lin1(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1, n_pairs);
+  if (int rc = lgcn_launch_linear(d2, st)) return rc;
+  // query = relu(GN(L(agts[hi])))  — a per-row function: computed per agent when that is fewer rows   :696
+  const float* q;
+  const int32_t* qidx;
+  if (n_agt <= n_pairs) {
+    LinearArgs qa = lin1(agts_in, nullptr, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, A0, n_agt);
+    if (int rc = lgcn_launch_linear(qa, st)) return rc;
+    q = A0; qidx = hi;
+  } else {
+    LinearArgs qp = lin1(agts_in, hi, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P2, n_pairs);
+    if (int rc = lgcn_launch_linear(qp, st)) return rc;
+    q = P2; qidx = nullptr;
+  }
+  // ctx = L(relu(GN(L384(cat(dist, query, ctx[wi])))))  — split-K over the three sources, no cat   :698-700
+  LinearArgs c0 = lin1(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0, n_pairs);
+  c0.n_src = 3;
+  c0.a[1] = q; c0.idx[1] = qidx;
+  c0.a[2] = ctx; c0.idx[2] = wi;
+  if (int rc = lgcn_launch_linear(c0, st)) return rc;
+  LinearArgs c1 = lin1(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1, n_pairs);
+  if (int rc = lgcn_launch_linear(c1, st)) return rc;
+  // agts = relu(GN(agt(agts) + scatter(ctx by hi)))                                                  :702-705
+  LinearArgs ag = lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1, n_agt);
+  if (int rc = lgcn_launch_linear(ag, st)) return rc;
+  if (int rc = lgcn_segsum_gn_relu(A1, P1, rowptr, w.ng, w.nb, A0, n_agt, stream)) return rc;
+  // agts = relu(GN(linear(agts)) + res)                                                              :707-709
+  LinearArgs l = lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt);
+  return lgcn_launch_linear(l, st);
+}

@@ -1,0 +1,193 @@
+// att.cu — the index side of Att (lanegcn.py:672-689: distance-thresholded pair list, batched, no per-scene
+// host sync) and the K=2 "first layer" MLP heads (lanegcn.py:277-286, 644-648, 693).
+#include "common.cuh"
+
+// scene owning global row r: largest b with off[b] <= r (off is ascending, may contain empty scenes)
+__device__ __forceinline__ int scene_of(const int32_t* __restrict__ off, int n_scenes, int32_t r) {
+  int lo = 0, hi = n_scenes;  // invariant: off[lo] <= r < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= r) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Bit-exact restatement of torch's  sqrt(((a - c) ** 2).sum(2)) <= th  in fp32: every operation rounded
+// separately (nvcc would otherwise contract dx*dx + dy*dy into an FMA and flip borderline pairs).
+__device__ __forceinline__ bool within(float ax, float ay, float cx, float cy, float th) {
+  const float dx = __fsub_rn(ax, cx), dy = __fsub_rn(ay, cy);
+  const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  return d <= th;
+}
+
+#define PAIR_WARPS 8
+
+// FILL == false: cnt[r] = number of context rows of r's scene within th.
+// FILL == true : write the pairs of row r at row_start[r].., hi = local row + hi_off[b], wi = j + wi_off[b].
+template <bool FILL>
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+k_pairs(const float2* __restrict__ agt_ctrs, const float2* __restrict__ ctx_ctrs,
+        const int32_t* __restrict__ agt_off, const int32_t* __restrict__ ctx_off, int n_scenes,
+        int64_t n_agt, float th, int32_t* __restrict__ cnt, const int32_t* __restrict__ row_start,
+        const int32_t* __restrict__ hi_off, const int32_t* __restrict__ wi_off, int32_t* __restrict__ hi32,
+        int32_t* __restrict__ wi32, int64_t* __restrict__ hi64, int64_t* __restrict__ wi64) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  if (r >= n_agt) return;
+  const int b = scene_of(agt_off, n_scenes, (int32_t)r);
+  const int32_t c0 = ctx_off[b], c1 = ctx_off[b + 1];
+  const float2 a = agt_ctrs[r];
+  int32_t run = 0;
+  int32_t pos = 0, h = 0, w0 = 0;
+  if (FILL) {
+    pos = row_start[r];
+    if (row_start[r + 1] == pos) return;  // nothing to write for this row
+    h = (int32_t)r - agt_off[b] + hi_off[b];
+    w0 = wi_off[b] - c0;
+  }
+  for (int32_t j0 = c0; j0 < c1; j0 += 32) {
+    const int32_t j = j0 + lane;
+    bool p = false;
+    if (j < c1) {
+      const float2 c = ctx_ctrs[j];
+      p = within(a.x, a.y, c.x, c.y, th);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (FILL && p) {
+      const int32_t o = pos + run + __popc(m & ((1u << lane) - 1u));
+      if (hi32) hi32[o] = h;
+      if (wi32) wi32[o] = j + w0;
+      if (hi64) hi64[o] = h;
+      if (wi64) wi64[o] = j + w0;
+    }
+    run += __popc(m);
+  }
+  if (!FILL && lane == 0) cnt[r] = run;
+}
+
+// Single CTA: per-scene totals from the scanned counts, then the reference's offset bookkeeping
+// (lanegcn.py:681-687: a scene without pairs `continue`s BEFORE hi_count/wi_count advance), then the
+// destination-indexed rowptr.  ws layout (int32): row_start[n_agt+1] | hi_off[B] | wi_off[B] | cnt[n_agt]
+__global__ void __launch_bounds__(1024)
+k_pairs_offsets(const int32_t* __restrict__ row_start, const int32_t* __restrict__ agt_off,
+                const int32_t* __restrict__ ctx_off, int n_scenes, int64_t n_agt, int keep_quirk,
+                int32_t* __restrict__ hi_off, int32_t* __restrict__ wi_off, int32_t* __restrict__ rowptr_dst) {
+  __shared__ int32_t used_rows;
+  const int32_t P = row_start[n_agt];
+  if (threadIdx.x == 0) {
+    int32_t hc = 0, wc = 0;
+    for (int b = 0; b < n_scenes; ++b) {
+      const int32_t tot = row_start[agt_off[b + 1]] - row_start[agt_off[b]];
+      if (keep_quirk) {
+        hi_off[b] = hc;
+        wi_off[b] = wc;
+        if (tot > 0) {
+          hc += agt_off[b + 1] - agt_off[b];
+          wc += ctx_off[b + 1] - ctx_off[b];
+        }
+      } else {
+        hi_off[b] = agt_off[b];
+        wi_off[b] = ctx_off[b];
+        hc = agt_off[b + 1];
+      }
+    }
+    used_rows = hc;
+  }
+  __syncthreads();
+  // destination row d = r - agt_off[b] + hi_off[b] for rows of scenes that have pairs (monotone, injective)
+  for (int64_t r = threadIdx.x; r < n_agt; r += blockDim.x) {
+    const int b = scene_of(agt_off, n_scenes, (int32_t)r);
+    const int32_t tot = row_start[agt_off[b + 1]] - row_start[agt_off[b]];
+    if (!keep_quirk || tot > 0) rowptr_dst[r - agt_off[b] + hi_off[b]] = row_start[r];
+  }
+  for (int64_t d = used_rows + threadIdx.x; d <= n_agt; d += blockDim.x) rowptr_dst[d] = P;
+}
+
+static inline int64_t pairs_ws_ints(int64_t n_agt, int n_scenes) {
+  return lgcn_align_up(n_agt + 1, 64) + 2 * lgcn_align_up(n_scenes, 64) + lgcn_align_up(n_agt, 64);
+}
+
+extern "C" int64_t lgcn_pairs_workspace_bytes(int64_t n_agt, int n_scenes) {
+  return 4 * pairs_ws_ints(n_agt, n_scenes) + 256;
+}
+
+extern "C" int lgcn_pairs_count(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off,
+                                const int32_t* ctx_off, int n_scenes, int64_t n_agt, float th, int keep_quirk,
+                                int32_t* rowptr, void* workspace, int64_t* h_total, void* stream) {
+  LGCN_CHECK_ARG(n_scenes >= 1 && n_agt >= 0, "pairs_count: n_scenes %d n_agt %lld", n_scenes, (long long)n_agt);
+  LGCN_CHECK_ARG(n_agt < (int64_t)1 << 31, "pairs_count: n_agt exceeds int32");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* row_start = (int32_t*)workspace;
+  int32_t* hi_off = row_start + lgcn_align_up(n_agt + 1, 64);
+  int32_t* wi_off = hi_off + lgcn_align_up(n_scenes, 64);
+  int32_t* cnt = wi_off + lgcn_align_up(n_scenes, 64);
+  if (n_agt > 0) {
+    k_pairs<false><<<lgcn_cdiv(n_agt, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(
+        (const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, th, cnt, nullptr,
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    LGCN_LAUNCH_OK();
+  }
+  if (lgcn_launch_exclusive_scan(cnt, row_start, n_agt, st)) return -2;
+  k_pairs_offsets<<<1, 1024, 0, st>>>(row_start, agt_off, ctx_off, n_scenes, n_agt, keep_quirk, hi_off, wi_off,
+                                      rowptr);
+  LGCN_LAUNCH_OK();
+  if (h_total) {
+    int32_t p = 0;
+    LGCN_CUDA_OK(cudaMemcpyAsync(&p, row_start + n_agt, 4, cudaMemcpyDeviceToHost, st));
+    LGCN_CUDA_OK(cudaStreamSynchronize(st));
+    *h_total = p;
+  }
+  return 0;
+}
+
+extern "C" int lgcn_pairs_fill(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off,
+                               const int32_t* ctx_off, int n_scenes, int64_t n_agt, float th,
+                               const void* workspace, int32_t* hi32, int32_t* wi32, int64_t* hi64,
+                               int64_t* wi64, void* stream) {
+  if (n_agt <= 0) return 0;
+  const int32_t* row_start = (const int32_t*)workspace;
+  const int32_t* hi_off = row_start + lgcn_align_up(n_agt + 1, 64);
+  const int32_t* wi_off = hi_off + lgcn_align_up(n_scenes, 64);
+  k_pairs<true><<<lgcn_cdiv(n_agt, PAIR_WARPS), PAIR_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      (const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, th, nullptr,
+      row_start, hi_off, wi_off, hi32, wi32, hi64, wi64);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ nn.Linear(2,128) + bias + ReLU heads
+// One warp per output row (512 B coalesced store); x = p[ip[m]] - q[iq[m]] for Att.dist (lanegcn.py:693).
+__global__ void __launch_bounds__(256)
+k_mlp2_in(const float2* __restrict__ p, const int32_t* __restrict__ ip, const float2* __restrict__ q,
+          const int32_t* __restrict__ iq, const float* __restrict__ W1, const float* __restrict__ b1,
+          float* __restrict__ h, int64_t m) {
+  const int lane = threadIdx.x & 31;
+  // W1 is [128,2] row-major: this lane's 4 output channels are rows lane*4..lane*4+3 = 8 contiguous floats
+  const float4 w01 = reinterpret_cast<const float4*>(W1)[lane * 2];
+  const float4 w23 = reinterpret_cast<const float4*>(W1)[lane * 2 + 1];
+  const float4 bb = reinterpret_cast<const float4*>(b1)[lane];
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < m; r += (int64_t)gridDim.x * 8) {
+    float2 x = p[ip ? ip[r] : r];
+    if (q) {
+      const float2 y = q[iq ? iq[r] : r];
+      x.x -= y.x;
+      x.y -= y.y;
+    }
+    float4 o;
+    // same association as addmm(bias, x, W^T): (x0*w0 + x1*w1) + b  — fp32, no reordering across terms
+    o.x = fmaxf(fmaf(x.y, w01.y, x.x * w01.x) + bb.x, 0.f);
+    o.y = fmaxf(fmaf(x.y, w01.w, x.x * w01.z) + bb.y, 0.f);
+    o.z = fmaxf(fmaf(x.y, w23.y, x.x * w23.x) + bb.z, 0.f);
+    o.w = fmaxf(fmaf(x.y, w23.w, x.x * w23.z) + bb.w, 0.f);
+    reinterpret_cast<float4*>(h + r * LGCN_C)[lane] = o;
+  }
+}
+
+extern "C" int lgcn_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq,
+                            const float* W1, const float* b1, float* h, int64_t m, void* stream) {
+  if (m <= 0) return 0;
+  const unsigned grid = min(lgcn_cdiv(m, 8), 148u * 32u);
+  k_mlp2_in<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)p, ip, (const float2*)q, iq, W1, b1, h, m);
+  LGCN_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,710 @@
+"""Drop-in for the reference ``lanegcn.py`` module API — forward graph path on B200 (sm_100a).
+
+Same names, constructor arguments, forward signatures, graph-dict keys, config keys and state_dict names
+as leepaul009/LaneGCN-1 ``lanegcn.py`` (Net :94-151, actor_gather :155-168, graph_gather :171-209,
+MapNet :266-363, A2M :366-407, M2M :410-480, M2A :483-513, A2A :516-545, Att :634-710, get_model :902-913),
+so reference checkpoints load by key and reference drivers can ``import_module`` this module instead.
+The modules only HOLD the parameters; every forward on the hot path is a call through the C ABI of
+``liblgcn_b200.so`` (include/lgcn.h) into hand-written CUDA.  Forward only (inference / no autograd);
+ActorNet and PredNet stay stock PyTorch (blocks.py) — they are off the hot path.
+
+There is no CPU path: tensors must live on a CUDA device and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _C
+from .blocks import ActorNet, Linear, PredNet
+
+# --------------------------------------------------------------------------- config (lanegcn.py:28-92)
+config = dict(
+    display_iters=205942, val_iters=205942 * 2, save_freq=1.0, epoch=0, horovod=False, opt="adam",
+    num_epochs=36, lr=[1e-3, 1e-4], lr_epochs=[32], batch_size=32, val_batch_size=32, workers=0,
+    val_workers=0, preprocess=True, rot_aug=False, pred_range=[-100.0, 100.0, -100.0, 100.0],
+    num_scales=6, n_actor=128, n_map=128, actor2map_dist=7.0, map2actor_dist=6.0, actor2actor_dist=100.0,
+    pred_size=30, pred_step=1, num_preds=30, num_mods=6, cls_coef=1.0, reg_coef=1.0, mgn=0.2, cls_th=2.0,
+    cls_ignore=0.2,
+)
+
+C_ = 128
+KEEP_PAIR_QUIRK = True  # reproduce the reference's empty-scene offset behaviour
+
+
+# --------------------------------------------------------------------------- small host-side helpers
+class SceneList(list):
+    """A list of per-scene tensors (what the reference passes around as ``*_idcs`` / ``*_ctrs``) that also
+    remembers the batched tensor it was split from and the scene offsets, so nothing is re-concatenated."""
+
+    cat: Optional[Tensor] = None       # the batched tensor the entries are views of
+    off: Optional[List[int]] = None    # python offsets, len B+1
+    off_dev: Optional[Tensor] = None   # int32 [B+1] on the device
+
+
+def scene_list(cat: Tensor, sizes: List[int], off_dev: Optional[Tensor] = None) -> SceneList:
+    out = SceneList(torch.split(cat, sizes))
+    out.cat = cat
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    out.off = off
+    out.off_dev = off_dev if off_dev is not None else torch.tensor(off, dtype=torch.int32, device=cat.device)
+    return out
+
+
+def _as_scene_list(lst, sizes: Optional[List[int]] = None) -> SceneList:
+    if isinstance(lst, SceneList) and lst.cat is not None:
+        return lst
+    lst = list(lst)
+    cat = torch.cat(lst, 0) if len(lst) else torch.zeros(0)
+    return scene_list(cat.contiguous(), [len(x) for x in lst] if sizes is None else sizes)
+
+
+class _Workspace:
+    """Grow-only scratch buffers, one per (device, tag); stream-ordered reuse on the current stream."""
+
+    _bufs: Dict = {}
+
+    @classmethod
+    def get(cls, nbytes: int, device, tag: str = "ws") -> Tensor:
+        key = (str(device), tag)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def _need_cuda(t: Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"lanegcn_b200: {what} must be a CUDA tensor (there is no CPU path)")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+class _WPack:
+    """Flat fp32 copy of a module's weights in the layout a fused C-ABI sequence expects; rebuilt when any
+    parameter changes (tensor ``_version`` bumps on in-place updates and on load_state_dict)."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, tensors: List[Tensor]) -> Tensor:
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key != self.key:
+            with torch.no_grad():
+                self.buf = torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
+            self.key = key
+        return self.buf
+
+
+# --------------------------------------------------------------------------- device-side graph container
+class PackedGraph:
+    """Batched graph on the device: node tensors + destination-sorted merged CSR over the edge sets in
+    accumulation order pre0,suc0,...,pre5,suc5,left,right (lanegcn.py:333-354)."""
+
+    def __init__(self):
+        self.n_nodes = 0
+        self.n_keys = 0
+        self.rowptr = None   # int32 [N+1]
+        self.col = None      # int32 [E]   col = v*(K+1) + (k+1)
+        self.err = None      # int32 [1]   non-zero if an index was out of range
+        self.meta = None     # f32 [N,4]   (turn0, turn1, control, intersect)
+        self.ctrs = None     # SceneList over f32 [N,2]
+        self.feats = None    # f32 [N,2]
+
+    def check(self):
+        """Synchronising validity check of the edge indices (tests / debugging)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("lanegcn_b200: graph edge index out of range [0, num_nodes)")
+
+
+def build_csr(edge_sets: List[Dict[str, Tensor]], n_nodes: int, device) -> PackedGraph:
+    """CSR from batched ``{u,v}`` int64 device tensors (in accumulation order)."""
+    lib = _C.lib()
+    K = len(edge_sets)
+    us = [e["u"].contiguous() for e in edge_sets]
+    vs = [e["v"].contiguous() for e in edge_sets]
+    for t in us + vs:
+        _need_cuda(t, "edge index")
+        if t.dtype != torch.int64:
+            raise RuntimeError("lanegcn_b200: batched edge indices must be int64 (as graph_gather returns them)")
+    lens = [int(u.numel()) for u in us]
+    E = sum(lens)
+    pg = PackedGraph()
+    pg.n_nodes, pg.n_keys = n_nodes, K
+    pg.rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=device)
+    pg.col = torch.empty(max(E, 1), dtype=torch.int32, device=device)
+    pg.err = torch.empty(1, dtype=torch.int32, device=device)
+    ws = _Workspace.get(lib.lgcn_csr_workspace_bytes(n_nodes, E), device, "csr")
+    PtrArr, LenArr = ctypes.c_void_p * K, ctypes.c_int64 * K
+    _C.check(
+        lib.lgcn_csr_build(PtrArr(*[u.data_ptr() for u in us]), PtrArr(*[v.data_ptr() for v in vs]),
+                           LenArr(*lens), K, n_nodes, pg.rowptr.data_ptr(), pg.col.data_ptr(), ws.data_ptr(),
+                           pg.err.data_ptr(), _C.stream_ptr()),
+        "csr_build",
+    )
+    pg._keep = (us, vs)
+    return pg
+
+
+def _edge_sets_of(graph: dict) -> List[Dict[str, Tensor]]:
+    sets = []
+    for s in range(len(graph["pre"])):
+        sets += [graph["pre"][s], graph["suc"][s]]
+    return sets + [graph["left"], graph["right"]]
+
+
+def _packed_of(graph: dict) -> PackedGraph:
+    """PackedGraph of a batched graph dict: the one graph_gather attached, or built from the dict's tensors
+    (so a graph dict produced by the reference's own graph_gather works too)."""
+    pg = graph.get("_packed")
+    if pg is not None:
+        return pg
+    feats = graph["feats"]
+    _need_cuda(feats, "graph['feats']")
+    n = feats.shape[0]
+    pg = build_csr(_edge_sets_of(graph), n, feats.device)
+    pg.feats = _f32c(feats)
+    pg.ctrs = _as_scene_list(graph["ctrs"])
+    pg.meta = torch.empty(n, 4, dtype=torch.float32, device=feats.device)
+    _C.check(_C.lib().lgcn_pack_meta(_f32c(graph["turn"]).data_ptr(), _f32c(graph["control"]).data_ptr(),
+                                     _f32c(graph["intersect"]).data_ptr(), pg.meta.data_ptr(), n,
+                                     _C.stream_ptr()), "pack_meta")
+    graph["_packed"] = pg
+    return pg
+
+
+# --------------------------------------------------------------------------- actor_gather / graph_gather
+def actor_gather(actors: List[Tensor]):
+    """lanegcn.py:155-168 — list of [A_i,20,3] -> ([sum A,3,20], per-scene index lists)."""
+    sizes = [len(x) for x in actors]
+    cat = torch.cat(list(actors), 0).transpose(1, 2).contiguous()
+    idcs = scene_list(torch.arange(sum(sizes), device=cat.device), sizes)
+    return cat, idcs
+
+
+class StagedGraphs:
+    """Per-scene graphs after the host->device copies and before any kernel: a float arena
+    [ctrs | feats | turn | control | intersect], the scene-local edge indices back to back in output order
+    (key, then u|v, then scene) and the segment table for the offset kernel."""
+
+    def __init__(self):
+        self.sizes: List[int] = []
+        self.off: List[int] = [0]
+        self.num_scales = 0
+        self.fl = self.local = self.segs = self.off_dev = None
+        self.seg_len: List[int] = []
+        self.h2d_bytes = 0
+
+
+def _edge_names(num_scales: int):
+    names = []
+    for s in range(num_scales):
+        names += [("pre", s), ("suc", s)]
+    return names + [("left", None), ("right", None)]
+
+
+def stage_graphs(graphs: List[dict]) -> StagedGraphs:
+    """Host side of graph_gather: concatenate the per-scene arrays into three staging buffers and issue one
+    H2D copy each (replaces ~38 cudaMemcpyAsync + 33 int16->int64 casts PER SCENE, utils.py:74-96)."""
+    sg = StagedGraphs()
+    sg.sizes = [int(g["num_nodes"]) for g in graphs]
+    for n in sg.sizes:
+        sg.off.append(sg.off[-1] + n)
+    sg.num_scales = len(graphs[0]["pre"])
+    dev = _target_device(graphs[0]["feats"])
+    parts = []
+    for key in ("ctrs", "feats", "turn", "control", "intersect"):
+        parts += [g[key].reshape(-1) for g in graphs]
+    sg.fl = _stage(torch.cat(parts), dev, torch.float32)
+    locs, seg_add = [], []
+    for k1, s in _edge_names(sg.num_scales):
+        for k2 in ("u", "v"):
+            for j, g in enumerate(graphs):
+                t = g[k1][k2] if s is None else g[k1][s][k2]
+                if t.dim() == 0:  # pickles where an empty array collapsed to a scalar (lanegcn.py:204-207)
+                    t = t.new_zeros(0)
+                locs.append(t)
+                seg_add.append(sg.off[j])
+    sg.seg_len = [t.numel() for t in locs]
+    dt = locs[0].dtype
+    if any(t.dtype != dt for t in locs):
+        dt, locs = torch.int64, [t.long() for t in locs]
+    if dt not in (torch.int16, torch.int32, torch.int64):
+        raise RuntimeError(f"lanegcn_b200: edge indices must be int16/int32/int64, got {dt}")
+    sg.local = _stage(torch.cat(locs), dev, dt)
+    seg_start = [0]
+    for n in sg.seg_len:
+        seg_start.append(seg_start[-1] + n)
+    sg.segs = _stage(torch.tensor(seg_start + seg_add, dtype=torch.int64), dev, torch.int64)
+    sg.off_dev = _stage(torch.tensor(sg.off, dtype=torch.int32), dev, torch.int32)
+    sg.h2d_bytes = sum(t.numel() * t.element_size() for t in (sg.fl, sg.local, sg.segs, sg.off_dev))
+    return sg
+
+
+def finish_graph(sg: StagedGraphs) -> dict:
+    """Device side of graph_gather: widen + offset the indices, assemble the reference's dict (views of
+    the arenas, no copies) and build the destination-sorted CSR."""
+    lib = _C.lib()
+    dev, N, B, sizes = sg.fl.device, sg.off[-1], len(sg.sizes), sg.sizes
+    fl = sg.fl
+    ctrs, feats, turn = fl[: 2 * N].view(N, 2), fl[2 * N: 4 * N].view(N, 2), fl[4 * N: 6 * N].view(N, 2)
+    control, intersect = fl[6 * N: 7 * N], fl[7 * N: 8 * N]
+    total, n_seg = int(sg.local.numel()), len(sg.seg_len)
+    e64 = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    _C.check(lib.lgcn_offset_indices(sg.local.data_ptr(), sg.local.element_size(), sg.segs.data_ptr(),
+                                     sg.segs[n_seg + 1:].data_ptr(), n_seg, total, e64.data_ptr(),
+                                     _C.stream_ptr()), "offset_indices")
+    graph = dict()
+    graph["idcs"] = scene_list(torch.arange(N, device=dev), sizes, sg.off_dev)
+    graph["ctrs"] = scene_list(ctrs, sizes, sg.off_dev)
+    graph["feats"], graph["turn"], graph["control"], graph["intersect"] = feats, turn, control, intersect
+    S = sg.num_scales
+    graph["pre"], graph["suc"] = [dict() for _ in range(S)], [dict() for _ in range(S)]
+    graph["left"], graph["right"] = dict(), dict()
+    pos, si = 0, 0
+    for k1, s in _edge_names(S):
+        for k2 in ("u", "v"):
+            n = sum(sg.seg_len[si: si + B])
+            (graph[k1] if s is None else graph[k1][s])[k2] = e64[pos: pos + n]
+            pos += n
+            si += B
+    pg = build_csr(_edge_sets_of(graph), N, dev)
+    pg.feats, pg.ctrs = feats, graph["ctrs"]
+    pg.meta = torch.empty(N, 4, dtype=torch.float32, device=dev)
+    _C.check(lib.lgcn_pack_meta(turn.data_ptr(), control.data_ptr(), intersect.data_ptr(), pg.meta.data_ptr(),
+                                N, _C.stream_ptr()), "pack_meta")
+    graph["_packed"] = pg
+    return graph
+
+
+def graph_gather(graphs: List[dict]) -> dict:
+    """lanegcn.py:171-209 (+ utils.to_long, utils.py:88-96): batch per-scene graphs.
+
+    Accepts the per-scene dicts with tensors on the CPU (int16/int32/int64 indices; staged through pinned
+    buffers with a handful of H2D copies in total) or already on the GPU.  Returns the reference's dict —
+    ``idcs``, ``ctrs`` (lists), ``feats/turn/control/intersect``, ``pre[s]/suc[s]/left/right`` ``{u,v}``
+    int64 — plus ``_packed`` (PackedGraph: the CSR the kernels use)."""
+    return finish_graph(stage_graphs(graphs))
+
+
+def _target_device(t: Tensor):
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("lanegcn_b200: no CUDA device (there is no CPU path)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stage(t: Tensor, dev, dtype) -> Tensor:
+    """CPU tensor -> pinned -> device with one async copy; device tensors pass through."""
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.is_cuda:
+        return t.contiguous()
+    return t.contiguous().pin_memory().to(dev, non_blocking=True)
+
+
+# --------------------------------------------------------------------------- Att pair lists
+class PairList:
+    """hi/wi (int32) + destination rowptr for one (agents, contexts, threshold) triple."""
+
+    def __init__(self, agt: SceneList, ctx: SceneList, th: float):
+        self.agt, self.ctx, self.th = agt, ctx, float(th)
+        self.n_agt, self.n_ctx = int(agt.cat.shape[0]), int(ctx.cat.shape[0])
+        dev = agt.cat.device
+        self.rowptr = torch.empty(self.n_agt + 1, dtype=torch.int32, device=dev)
+        self.ws = torch.empty(_C.lib().lgcn_pairs_workspace_bytes(self.n_agt, len(agt)), dtype=torch.uint8, device=dev)
+        self.n_pairs = None
+        self.hi = self.wi = None
+
+    def count(self):
+        _C.check(_C.lib().lgcn_pairs_count(self.agt.cat.data_ptr(), self.ctx.cat.data_ptr(),
+                                           self.agt.off_dev.data_ptr(), self.ctx.off_dev.data_ptr(), len(self.agt),
+                                           self.n_agt, self.th, int(KEEP_PAIR_QUIRK), self.rowptr.data_ptr(),
+                                           self.ws.data_ptr(), None, _C.stream_ptr()), "pairs_count")
+
+    def fill(self, n_pairs: int, want_int64: bool = False):
+        dev = self.agt.cat.device
+        self.n_pairs = int(n_pairs)
+        self.hi = torch.empty(max(self.n_pairs, 1), dtype=torch.int32, device=dev)
+        self.wi = torch.empty(max(self.n_pairs, 1), dtype=torch.int32, device=dev)
+        self.hi64 = torch.empty(self.n_pairs, dtype=torch.int64, device=dev) if want_int64 else None
+        self.wi64 = torch.empty(self.n_pairs, dtype=torch.int64, device=dev) if want_int64 else None
+        if self.n_pairs:
+            _C.check(_C.lib().lgcn_pairs_fill(self.agt.cat.data_ptr(), self.ctx.cat.data_ptr(),
+                                              self.agt.off_dev.data_ptr(), self.ctx.off_dev.data_ptr(),
+                                              len(self.agt), self.n_agt, self.th, self.ws.data_ptr(),
+                                              self.hi.data_ptr(), self.wi.data_ptr(), _C.ptr(self.hi64),
+                                              _C.ptr(self.wi64), _C.stream_ptr()), "pairs_fill")
+        return self
+
+
+def build_pair_lists(specs, want_int64: bool = False) -> List[PairList]:
+    """Pair lists for several (agt_ctrs, ctx_ctrs, th) triples with ONE host synchronisation in total
+    (the reference synchronises once per scene per Att layer: lanegcn.py:680-681)."""
+    pls = [PairList(_as_scene_list(a), _as_scene_list(c), th) for a, c, th in specs]
+    for p in pls:
+        _need_cuda(p.agt.cat, "agent centres")
+        p.count()
+    totals = torch.stack([p.rowptr[-1] for p in pls]).tolist()  # the one D2H sync
+    for p, n in zip(pls, totals):
+        p.fill(n, want_int64)
+    return pls
+
+
+def att_pairs(agt_ctrs, ctx_ctrs, dist_th: float):
+    """(hi, wi) int64 exactly as lanegcn.py:672-689 builds them (bit-exact, incl. the empty-scene quirk)."""
+    p = build_pair_lists([(agt_ctrs, ctx_ctrs, dist_th)], want_int64=True)[0]
+    return p.hi64, p.wi64
+
+
+# --------------------------------------------------------------------------- LaneConv stack (MapNet / M2M)
+def _fuse_modules(n_map: int, num_scales: int) -> nn.ModuleDict:
+    """Parameter tree of lanegcn.py:288-309: insertion order ctr,norm,ctr2,left,right,pre0,suc0,... matters
+    only for state_dict order; the accumulation order is fixed by the kernels' key order."""
+    keys = ["ctr", "norm", "ctr2", "left", "right"]
+    for s in range(num_scales):
+        keys += [f"pre{s}", f"suc{s}"]
+    fuse = {}
+    for key in keys:
+        if key == "norm":
+            fuse[key] = nn.ModuleList([nn.GroupNorm(1, n_map) for _ in range(4)])
+        elif key == "ctr2":
+            fuse[key] = nn.ModuleList([Linear(n_map, n_map, act=False) for _ in range(4)])
+        else:
+            fuse[key] = nn.ModuleList([nn.Linear(n_map, n_map, bias=False) for _ in range(4)])
+    return nn.ModuleDict(fuse)
+
+
+class _LaneConvStack(nn.Module):
+    """The 4-block LaneConv loop (lanegcn.py:331-362 == :448-479) as one C-ABI call."""
+
+    def _init_fuse(self, config):
+        self.config = config
+        self.num_scales = config["num_scales"]
+        self.fuse = _fuse_modules(config["n_map"], self.num_scales)
+        self._wp = _WPack()
+
+    def _edge_keys(self) -> List[str]:
+        keys = []
+        for s in range(self.num_scales):
+            keys += [f"pre{s}", f"suc{s}"]
+        return keys + ["left", "right"]
+
+    def _wpack(self) -> Tensor:
+        ts = []
+        for i in range(4):
+            ts.append(self.fuse["ctr"][i].weight)
+            ts += [self.fuse[k][i].weight for k in self._edge_keys()]
+            ts += [self.fuse["ctr2"][i].linear.weight, self.fuse["norm"][i].weight, self.fuse["norm"][i].bias,
+                   self.fuse["ctr2"][i].norm.weight, self.fuse["ctr2"][i].norm.bias]
+        return self._wp.get(ts)
+
+    def _stack(self, feat: Tensor, pg: PackedGraph) -> Tensor:
+        lib = _C.lib()
+        K = len(self._edge_keys())
+        if pg.n_keys != K:
+            raise RuntimeError(f"lanegcn_b200: graph has {pg.n_keys} edge sets, model expects {K}")
+        n = feat.shape[0]
+        ws = _Workspace.get(lib.lgcn_laneconv_workspace_bytes(n, K), feat.device, "laneconv")
+        _C.check(lib.lgcn_laneconv_stack(feat.data_ptr(), pg.rowptr.data_ptr(), pg.col.data_ptr(), K, 4,
+                                         self._wpack().data_ptr(), n, ws.data_ptr(), _C.stream_ptr()),
+                 "laneconv_stack")
+        return feat
+
+
+class MapNet(_LaneConvStack):
+    """Map graph feature extractor (lanegcn.py:266-363)."""
+
+    def __init__(self, config):
+        super().__init__()
+        n = config["n_map"]
+        self.input = nn.Sequential(nn.Linear(2, n), nn.ReLU(inplace=True), Linear(n, n, act=False))
+        self.seg = nn.Sequential(nn.Linear(2, n), nn.ReLU(inplace=True), Linear(n, n, act=False))
+        self._init_fuse(config)
+        self.relu = nn.ReLU(inplace=True)
+
+    @torch.no_grad()
+    def forward(self, graph):
+        if len(graph["feats"]) == 0 or len(graph["pre"][-1]["u"]) == 0 or len(graph["suc"][-1]["u"]) == 0:
+            # the reference's degenerate-graph branch reads a key graph_gather never sets (lanegcn.py:320)
+            raise KeyError("node_idcs")
+        lib, st = _C.lib(), _C.stream_ptr()
+        pg = _packed_of(graph)
+        n, dev = pg.n_nodes, pg.feats.device
+        hid = torch.empty(n, C_, dtype=torch.float32, device=dev)
+        a = torch.empty(n, C_, dtype=torch.float32, device=dev)
+        feat = torch.empty(n, C_, dtype=torch.float32, device=dev)
+        # feat = relu(input(ctrs) + seg(feats))                                      lanegcn.py:324-327
+        for src, mlp, res, flags, out in (
+            (pg.ctrs.cat, self.input, None, _C.EPI_GN, a),
+            (pg.feats, self.seg, a, _C.EPI_GN | _C.EPI_RES | _C.EPI_RELU2, feat),
+        ):
+            _C.check(lib.lgcn_mlp2_in(src.data_ptr(), None, None, None, mlp[0].weight.data_ptr(),
+                                      mlp[0].bias.data_ptr(), hid.data_ptr(), n, st), "mlp2_in")
+            _C.check(lib.lgcn_linear128(hid.data_ptr(), None, None, None, None, None, 1, None, 0,
+                                        mlp[2].linear.weight.data_ptr(), 1, mlp[2].norm.weight.data_ptr(),
+                                        mlp[2].norm.bias.data_ptr(), _C.ptr(res), flags, out.data_ptr(), C_, n,
+                                        st), "linear128")
+        feat = self._stack(feat, pg)
+        return feat, graph["idcs"], graph["ctrs"]
+
+
+class M2M(_LaneConvStack):
+    """Lane-to-lane propagation (lanegcn.py:410-480): the same 4-block LaneConv loop."""
+
+    def __init__(self, config):
+        super().__init__()
+        self._init_fuse(config)
+        self.relu = nn.ReLU(inplace=True)
+
+    @torch.no_grad()
+    def forward(self, feat: Tensor, graph: Dict) -> Tensor:
+        _need_cuda(feat, "feat")
+        return self._stack(_f32c(feat).clone(), _packed_of(graph))
+
+
+# --------------------------------------------------------------------------- Att and its three users
+class Att(nn.Module):
+    """Attention block passing context-node information to target nodes (lanegcn.py:634-710)."""
+
+    def __init__(self, n_agt: int, n_ctx: int) -> None:
+        super().__init__()
+        if n_agt != C_ or n_ctx != C_:
+            raise ValueError("lanegcn_b200: Att kernels are built for n_agt = n_ctx = 128 (reference config)")
+        self.dist = nn.Sequential(nn.Linear(2, n_ctx), nn.ReLU(inplace=True), Linear(n_ctx, n_ctx))
+        self.query = Linear(n_agt, n_ctx)
+        self.ctx = nn.Sequential(Linear(3 * n_ctx, n_agt), nn.Linear(n_agt, n_agt, bias=False))
+        self.agt = nn.Linear(n_agt, n_agt, bias=False)
+        self.norm = nn.GroupNorm(1, n_agt)
+        self.linear = Linear(n_agt, n_agt, act=False)
+        self.relu = nn.ReLU(inplace=True)
+        self._wp = _WPack()
+
+    def _wpack(self) -> Tensor:
+        return self._wp.get([
+            self.dist[0].weight, self.dist[0].bias, self.dist[2].linear.weight, self.dist[2].norm.weight,
+            self.dist[2].norm.bias, self.query.linear.weight, self.query.norm.weight, self.query.norm.bias,
+            self.ctx[0].linear.weight, self.ctx[0].norm.weight, self.ctx[0].norm.bias, self.ctx[1].weight,
+            self.agt.weight, self.norm.weight, self.norm.bias, self.linear.linear.weight,
+            self.linear.norm.weight, self.linear.norm.bias,
+        ])
+
+    @torch.no_grad()
+    def forward(self, agts: Tensor, agt_idcs: List[Tensor], agt_ctrs: List[Tensor], ctx: Tensor,
+                ctx_idcs: List[Tensor], ctx_ctrs: List[Tensor], dist_th: float,
+                pairs: Optional[PairList] = None) -> Tensor:
+        lib = _C.lib()
+        _need_cuda(agts, "agts")
+        agts, ctx = _f32c(agts), _f32c(ctx)
+        n_agt, n_ctx = agts.shape[0], ctx.shape[0]
+        out = torch.empty_like(agts)
+        if n_ctx == 0:
+            ws = _Workspace.get(lib.lgcn_att_workspace_bytes(n_agt, 0), agts.device, "att")
+            _C.check(lib.lgcn_att_forward(agts.data_ptr(), out.data_ptr(), None, None, None, None, None, None,
+                                          n_agt, 0, 0, self._wpack().data_ptr(), ws.data_ptr(),
+                                          _C.stream_ptr()), "att_forward")
+            return out
+        if pairs is None:
+            a = _as_scene_list(agt_ctrs, [len(x) for x in agt_idcs])
+            c = _as_scene_list(ctx_ctrs, [len(x) for x in ctx_idcs])
+            pairs = build_pair_lists([(a, c, dist_th)])[0]
+        if pairs.n_pairs == 0:
+            raise RuntimeError("lanegcn_b200: Att found no agent/context pair within dist_th in any scene "
+                               "(the reference raises here too: torch.cat of an empty list, lanegcn.py:688)")
+        ws = _Workspace.get(lib.lgcn_att_workspace_bytes(n_agt, pairs.n_pairs), agts.device, "att")
+        _C.check(lib.lgcn_att_forward(agts.data_ptr(), out.data_ptr(), ctx.data_ptr(), pairs.agt.cat.data_ptr(),
+                                      pairs.ctx.cat.data_ptr(), pairs.hi.data_ptr(), pairs.wi.data_ptr(),
+                                      pairs.rowptr.data_ptr(), n_agt, n_ctx, pairs.n_pairs,
+                                      self._wpack().data_ptr(), ws.data_ptr(), _C.stream_ptr()), "att_forward")
+        return out
+
+
+def _shared_pairs(agt_idcs, agt_ctrs, ctx_idcs, ctx_ctrs, th, pairs):
+    """Both Att layers of a block see the same centres: build the list once (the reference rebuilds it)."""
+    if pairs is not None:
+        return pairs
+    a = _as_scene_list(agt_ctrs, [len(x) for x in agt_idcs])
+    c = _as_scene_list(ctx_ctrs, [len(x) for x in ctx_idcs])
+    return build_pair_lists([(a, c, th)])[0]
+
+
+class A2M(nn.Module):
+    """Actor-to-map fusion (lanegcn.py:366-407)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        n_map = config["n_map"]
+        self.meta = Linear(n_map + 4, n_map)
+        self.att = nn.ModuleList([Att(n_map, config["n_actor"]) for _ in range(2)])
+
+    @torch.no_grad()
+    def forward(self, feat: Tensor, graph: Dict, actors: Tensor, actor_idcs: List[Tensor],
+                actor_ctrs: List[Tensor], pairs: Optional[PairList] = None) -> Tensor:
+        lib = _C.lib()
+        pg = _packed_of(graph)
+        feat = _f32c(feat)
+        n = feat.shape[0]
+        out = torch.empty_like(feat)
+        # feat = relu(GN(Linear_132->128(cat(feat, turn, control, intersect))))        lanegcn.py:387-395
+        _C.check(lib.lgcn_linear128(feat.data_ptr(), None, None, None, None, None, 1, pg.meta.data_ptr(), 4,
+                                    self.meta.linear.weight.data_ptr(), 1, self.meta.norm.weight.data_ptr(),
+                                    self.meta.norm.bias.data_ptr(), None, _C.EPI_GN | _C.EPI_RELU1,
+                                    out.data_ptr(), C_, n, _C.stream_ptr()), "linear128(meta)")
+        feat = out
+        pairs = _shared_pairs(graph["idcs"], graph["ctrs"], actor_idcs, actor_ctrs, self.config["actor2map_dist"], pairs)
+        for att in self.att:
+            feat = att(feat, graph["idcs"], graph["ctrs"], actors, actor_idcs, actor_ctrs,
+                       self.config["actor2map_dist"], pairs=pairs)
+        return feat
+
+
+class M2A(nn.Module):
+    """Map-to-actor fusion (lanegcn.py:483-513)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.att = nn.ModuleList([Att(config["n_actor"], config["n_map"]) for _ in range(2)])
+
+    @torch.no_grad()
+    def forward(self, actors: Tensor, actor_idcs: List[Tensor], actor_ctrs: List[Tensor], nodes: Tensor,
+                node_idcs: List[Tensor], node_ctrs: List[Tensor], pairs: Optional[PairList] = None) -> Tensor:
+        th = self.config["map2actor_dist"]
+        pairs = _shared_pairs(actor_idcs, actor_ctrs, node_idcs, node_ctrs, th, pairs)
+        for att in self.att:
+            actors = att(actors, actor_idcs, actor_ctrs, nodes, node_idcs, node_ctrs, th, pairs=pairs)
+        return actors
+
+
+class A2A(nn.Module):
+    """Actor-to-actor interaction (lanegcn.py:516-545)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.att = nn.ModuleList([Att(config["n_actor"], config["n_actor"]) for _ in range(2)])
+
+    @torch.no_grad()
+    def forward(self, actors: Tensor, actor_idcs: List[Tensor], actor_ctrs: List[Tensor],
+                pairs: Optional[PairList] = None) -> Tensor:
+        th = self.config["actor2actor_dist"]
+        pairs = _shared_pairs(actor_idcs, actor_ctrs, actor_idcs, actor_ctrs, th, pairs)
+        for att in self.att:
+            actors = att(actors, actor_idcs, actor_ctrs, actors, actor_idcs, actor_ctrs, th, pairs=pairs)
+        return actors
+
+
+# --------------------------------------------------------------------------- Net
+class DeviceBatch:
+    """A collated batch after its host->device copies and before any kernel: the input of
+    ``Net.forward_device`` (the device-resident timing) — ``Net.stage`` builds it."""
+
+    def __init__(self):
+        self.actors = None       # f32 [sum A, 20, 3] (transposed on the device)
+        self.actor_ctrs = None   # SceneList over f32 [sum A, 2]
+        self.graphs = None       # StagedGraphs
+        self.rot = None          # f32 [B,2,2]
+        self.orig = None         # f32 [B,2]
+        self.h2d_bytes = 0
+
+
+class Net(nn.Module):
+    """LaneGCN (lanegcn.py:94-151): ActorNet, MapNet, A2M -> M2M -> M2A -> A2A, PredNet."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.actor_net = ActorNet(config)
+        self.map_net = MapNet(config)
+        self.a2m = A2M(config)
+        self.m2m = M2M(config)
+        self.m2a = M2A(config)
+        self.a2a = A2A(config)
+        self.pred_net = PredNet(config)
+
+    def _device(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("lanegcn_b200: move the model to a CUDA device first (there is no CPU path)")
+        return dev
+
+    def stage(self, data: Dict) -> DeviceBatch:
+        """Host packing + H2D of one collated batch (what utils.gpu does tensor by tensor, utils.py:74-85)."""
+        dev = self._device()
+        with torch.cuda.device(dev):
+            b = DeviceBatch()
+            sizes = [len(x) for x in data["feats"]]
+            b.actors = _stage(torch.cat(list(data["feats"]), 0), dev, torch.float32)
+            b.actor_ctrs = scene_list(_stage(torch.cat(list(data["ctrs"]), 0), dev, torch.float32), sizes)
+            b.rot = _stage(torch.stack(list(data["rot"])), dev, torch.float32)
+            b.orig = _stage(torch.stack(list(data["orig"])), dev, torch.float32)
+            b.graphs = stage_graphs(data["graph"])
+            b.h2d_bytes = b.graphs.h2d_bytes + 4 * (b.actors.numel() + b.actor_ctrs.cat.numel() + b.rot.numel()
+                                                    + b.orig.numel()) + 4 * (len(sizes) + 1)
+            return b
+
+    @torch.no_grad()
+    def forward(self, data: Dict) -> Dict[str, List[Tensor]]:
+        return self.forward_device(self.stage(data))
+
+    @torch.no_grad()
+    def forward_device(self, b: DeviceBatch) -> Dict[str, List[Tensor]]:
+        cfg = self.config
+        with torch.cuda.device(b.actors.device):
+            actor_ctrs = b.actor_ctrs
+            sizes = [len(x) for x in actor_ctrs]
+            actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev)
+            graph = finish_graph(b.graphs)                                        # lanegcn.py:134
+            node_ctrs = graph["ctrs"]
+            # the three pair lists depend on centres only: build them up front with ONE host sync
+            p_a2m, p_m2a, p_a2a = build_pair_lists([
+                (node_ctrs, actor_ctrs, cfg["actor2map_dist"]),
+                (actor_ctrs, node_ctrs, cfg["map2actor_dist"]),
+                (actor_ctrs, actor_ctrs, cfg["actor2actor_dist"]),
+            ])
+            actors = self.actor_net(b.actors.transpose(1, 2).contiguous())        # :129-131
+            nodes, node_idcs, node_ctrs = self.map_net(graph)                     # :135
+            nodes = self.a2m(nodes, graph, actors, actor_idcs, actor_ctrs, pairs=p_a2m)   # :138
+            nodes = self.m2m(nodes, graph)                                        # :139
+            actors = self.m2a(actors, actor_idcs, actor_ctrs, nodes, node_idcs, node_ctrs, pairs=p_m2a)  # :140
+            actors = self.a2a(actors, actor_idcs, actor_ctrs, pairs=p_a2a)        # :141
+            out = self.pred_net(actors, actor_idcs, actor_ctrs)                   # :144
+            # world transform (lanegcn.py:145-150), batched: every actor uses its scene's rot/orig
+            scene_of_actor = torch.repeat_interleave(
+                torch.arange(len(sizes), device=b.rot.device), torch.tensor(sizes, device=b.rot.device),
+                output_size=sum(sizes))
+            reg = torch.cat(out["reg"], 0)
+            reg = torch.matmul(reg, b.rot[scene_of_actor].unsqueeze(1)) + b.orig[scene_of_actor].view(-1, 1, 1, 2)
+            out["reg"] = list(torch.split(reg, sizes))
+            return out
+
+
+def get_model():
+    """lanegcn.py:902-913 shape: (config, Dataset, collate_fn, net, loss, post_process, opt).
+    Training pieces (loss, post_process, optimiser) are outside the forward path: returned as None."""
+    from . import synth
+
+    net = Net(config).cuda()
+
+    class SynthDataset(torch.utils.data.Dataset):
+        def __init__(self, split=None, config=None, train=False, length=1024, preset="argo-1.5k"):
+            self.length, self.preset = length, preset
+
+        def __len__(self):
+            return self.length
+
+        def __getitem__(self, idx):
+            return synth.make_scene(idx, self.preset)
+
+    return config, SynthDataset, synth.collate, net, None, None, None

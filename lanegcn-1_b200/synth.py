@@ -208,3 +208,25 @@ def collate(scenes):
     (same result as reference data.py:555-575 ``collate_fn``, without mutating the inputs)."""
     scenes = [_to_torch(s) for s in scenes]
     return {key: [s[key] for s in scenes] for key in scenes[0].keys()}
+
+
+def seeded_state_dict(shapes: dict, seed: int = 0):
+    """Deterministic, platform-independent weights for a {name: shape} table (numpy RNG, not torch's, so the
+    authoring container and the GPU box produce identical tensors without shipping a 15 MB checkpoint).
+    Linear/conv weights ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)); GroupNorm weight ~ 1 + 0.1 N(0,1) and every
+    bias ~ 0.1 N(0,1), so the affine terms are exercised (torch's default init has weight=1, bias=0)."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        if len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            w = rng.uniform(-1.0, 1.0, shape) / np.sqrt(fan_in)
+        elif name.endswith("weight"):
+            w = 1.0 + 0.1 * rng.standard_normal(shape)
+        else:
+            w = 0.1 * rng.standard_normal(shape)
+        out[name] = torch.from_numpy(w.astype(np.float32))
+    return out

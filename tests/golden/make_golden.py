@@ -1,0 +1,131 @@
+"""Golden fixtures from the UNMODIFIED reference (leepaul009/LaneGCN-1), run on CPU fp32 in the authoring
+container.  Needs /root/reference; the GPU box and the driver's CPU test run only read the committed files.
+
+    python tests/golden/make_golden.py
+
+Writes (tests/golden/):
+  state_dict_shapes.json   name -> shape of the reference Net's 405 state_dict entries (App. A.6 contract)
+  tiny_b3.npz             batch of 3 "tiny" scenes (N=180 each; the middle scene's actors moved far away so
+                           A2M/M2A see an EMPTY scene -> exercises the offset quirk):
+                           per-stage outputs (forward hooks), cls/reg, graph_gather outputs, every pair list
+  argo_b1.npz              config 1 (one argo-1.5k scene): cls/reg + per-stage checksums + pair lists
+  dilate_tiny.npz         reference data.dilated_nbrs output for scene 0's pre/suc scale-0 edges
+Inputs and weights are NOT stored: both sides regenerate them from seeds (synth.make_scenes / seeded_state_dict).
+"""
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from lanegcn_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAGES = ["actor_net", "map_net", "a2m", "m2m", "m2a", "a2a"]
+
+
+def golden_scenes(name):
+    if name == "tiny_b3":
+        scenes = synth.make_scenes(3, "tiny", seed0=100)
+        scenes[1]["ctrs"] = scenes[1]["ctrs"] + np.float32(5000.0)  # no node within 7 m / 6 m of any actor
+        return scenes
+    if name == "argo_b1":
+        return synth.make_scenes(1, "argo-1.5k", seed0=0)
+    raise KeyError(name)
+
+
+def run_reference(net, ref_lanegcn, ref_data, scenes):
+    batch = ref_data.collate_fn(copy.deepcopy(scenes))
+    taps, pairs = {}, []
+    hooks = []
+    for s in STAGES:
+        hooks.append(getattr(net, s).register_forward_hook(
+            lambda m, i, o, s=s: taps.__setitem__(s, (o[0] if isinstance(o, tuple) else o).detach().clone())))
+    orig_index_add = torch.Tensor.index_add_
+
+    def spy(self, dim, index, src, *a, **k):
+        pairs.append(index.detach().clone())
+        return orig_index_add(self, dim, index, src, *a, **k)
+
+    torch.Tensor.index_add_ = spy
+    try:
+        with torch.no_grad():
+            out = net(batch)
+    finally:
+        torch.Tensor.index_add_ = orig_index_add
+        for h in hooks:
+            h.remove()
+    graph = ref_lanegcn.graph_gather(ref_lanegcn.to_long(ref_data.collate_fn(copy.deepcopy(scenes))["graph"]))
+    return out, taps, pairs, graph
+
+
+def main():
+    ref_lanegcn, ref_data = ref_loader.load()
+    torch.manual_seed(0)
+    net = ref_lanegcn.Net(ref_lanegcn.config).eval()
+    shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    json.dump(shapes, open(os.path.join(HERE, "state_dict_shapes.json"), "w"), indent=0, sort_keys=True)
+    net.load_state_dict(synth.seeded_state_dict(shapes, seed=0))
+
+    for name in ("tiny_b3", "argo_b1"):
+        scenes = golden_scenes(name)
+        out, taps, idx_log, graph = run_reference(net, ref_lanegcn, ref_data, scenes)
+        rec = {"cls": torch.cat(out["cls"]).numpy(), "reg": torch.cat(out["reg"]).numpy()}
+        # Att scatter indices (hi) in call order: 14 index_add_ per LaneConv block x 4 blocks for MapNet, then
+        # A2M's two Att layers, M2M's 56, M2A's two, A2A's two  (lanegcn.py:702-703)
+        n_lc = 14 * 4
+        att_hi = [idx_log[n_lc], idx_log[n_lc + 2 + n_lc], idx_log[n_lc + 2 + n_lc + 2]]
+        for tag, hi in zip(("a2m", "m2a", "a2a"), att_hi):
+            rec[f"hi_{tag}"] = hi.numpy()
+        # wi is not passed to index_add_: recompute both with the reference's own expression sequence
+        batch = ref_data.collate_fn(copy.deepcopy(scenes))
+        nctr, actr = [g["ctrs"] for g in batch["graph"]], batch["ctrs"]
+        for tag, (a, c, th) in {"a2m": (nctr, actr, 7.0), "m2a": (actr, nctr, 6.0), "a2a": (actr, actr, 100.0)}.items():
+            hi, wi, hc, wc = [], [], 0, 0
+            for x, y in zip(a, c):
+                d = x.view(-1, 1, 2) - y.view(1, -1, 2)
+                d = torch.sqrt((d ** 2).sum(2))
+                idcs = torch.nonzero(d <= th, as_tuple=False)
+                if len(idcs) == 0:
+                    continue
+                hi.append(idcs[:, 0] + hc); wi.append(idcs[:, 1] + wc)
+                hc += len(x); wc += len(y)
+            assert torch.equal(torch.cat(hi), torch.from_numpy(rec[f"hi_{tag}"])), tag
+            rec[f"wi_{tag}"] = torch.cat(wi).numpy()
+        if name == "tiny_b3":
+            for s in STAGES:
+                rec[f"stage_{s}"] = taps[s].numpy()
+            for k1 in ("pre", "suc"):
+                for i in range(6):
+                    for k2 in ("u", "v"):
+                        rec[f"g_{k1}{i}_{k2}"] = graph[k1][i][k2].numpy()
+            for k1 in ("left", "right"):
+                for k2 in ("u", "v"):
+                    rec[f"g_{k1}_{k2}"] = graph[k1][k2].numpy()
+            for k in ("feats", "turn", "control", "intersect"):
+                rec[f"g_{k}"] = graph[k].numpy()
+        else:
+            for s in STAGES:  # full tensors would be 0.8 MB each: keep a strided sample + float64 sums
+                t = taps[s].double()
+                rec[f"sum_{s}"] = np.asarray([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+                rec[f"rows_{s}"] = taps[s][::37].numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+        print(name, {k: v.shape for k, v in rec.items() if not k.startswith("g_")})
+
+    g = golden_scenes("tiny_b3")[0]["graph"]
+    rec = {}
+    for d in ("pre", "suc"):
+        ref = ref_data.dilated_nbrs({"u": g[d][0]["u"].astype(np.int64), "v": g[d][0]["v"].astype(np.int64)},
+                                    g["num_nodes"], 6)
+        for i, e in enumerate(ref):
+            rec[f"{d}{i + 1}_u"], rec[f"{d}{i + 1}_v"] = e["u"], e["v"]
+    np.savez_compressed(os.path.join(HERE, "dilate_tiny.npz"), **rec)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""Shared test helpers: golden inputs, seeded weights, tolerances."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from lanegcn_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# north_star tolerance for float outputs: within 1e-4 relative / 1e-5 absolute of the reference fp32 forward
+RTOL, ATOL = 1e-4, 1e-5
+STAGES = ["actor_net", "map_net", "a2m", "m2m", "m2a", "a2a"]
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def shapes():
+    return json.load(open(os.path.join(GOLDEN, "state_dict_shapes.json")))
+
+
+def weights(seed=0):
+    return synth.seeded_state_dict(shapes(), seed)
+
+
+def golden_scenes(name):
+    """Must mirror tests/golden/make_golden.py::golden_scenes."""
+    if name == "tiny_b3":
+        scenes = synth.make_scenes(3, "tiny", seed0=100)
+        scenes[1]["ctrs"] = scenes[1]["ctrs"] + np.float32(5000.0)
+        return scenes
+    if name == "argo_b1":
+        return synth.make_scenes(1, "argo-1.5k", seed0=0)
+    raise KeyError(name)
+
+
+def assert_close(got, want, what="", rtol=RTOL, atol=ATOL):
+    got = torch.as_tensor(got).detach().cpu().double()
+    want = torch.as_tensor(want).detach().cpu().double()
+    assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = err > tol
+    assert not bool(bad.any()), (
+        f"{what}: {int(bad.sum())}/{bad.numel()} elements outside rtol={rtol} atol={atol}; "
+        f"max abs err {err.max().item():.3e}, max err/tol {(err / tol).max().item():.2f}"
+    )
