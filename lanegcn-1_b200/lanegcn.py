@@ -616,6 +616,7 @@ class DeviceBatch:
         self.graphs = None       # StagedGraphs
         self.rot = None          # f32 [B,2,2]
         self.orig = None         # f32 [B,2]
+        self.scene_of_actor = None  # int64 [sum A]
         self.h2d_bytes = 0
 
 
@@ -649,9 +650,11 @@ class Net(nn.Module):
             b.actor_ctrs = scene_list(_stage(torch.cat(list(data["ctrs"]), 0), dev, torch.float32), sizes)
             b.rot = _stage(torch.stack(list(data["rot"])), dev, torch.float32)
             b.orig = _stage(torch.stack(list(data["orig"])), dev, torch.float32)
+            b.scene_of_actor = _stage(torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes)), dev,
+                                      torch.int64)
             b.graphs = stage_graphs(data["graph"])
             b.h2d_bytes = b.graphs.h2d_bytes + 4 * (b.actors.numel() + b.actor_ctrs.cat.numel() + b.rot.numel()
-                                                    + b.orig.numel()) + 4 * (len(sizes) + 1)
+                                                    + b.orig.numel()) + 4 * (len(sizes) + 1) + 8 * b.scene_of_actor.numel()
             return b
 
     @torch.no_grad()
@@ -681,11 +684,8 @@ class Net(nn.Module):
             actors = self.a2a(actors, actor_idcs, actor_ctrs, pairs=p_a2a)        # :141
             out = self.pred_net(actors, actor_idcs, actor_ctrs)                   # :144
             # world transform (lanegcn.py:145-150), batched: every actor uses its scene's rot/orig
-            scene_of_actor = torch.repeat_interleave(
-                torch.arange(len(sizes), device=b.rot.device), torch.tensor(sizes, device=b.rot.device),
-                output_size=sum(sizes))
             reg = torch.cat(out["reg"], 0)
-            reg = torch.matmul(reg, b.rot[scene_of_actor].unsqueeze(1)) + b.orig[scene_of_actor].view(-1, 1, 1, 2)
+            reg = torch.matmul(reg, b.rot[b.scene_of_actor].unsqueeze(1)) + b.orig[b.scene_of_actor].view(-1, 1, 1, 2)
             out["reg"] = list(torch.split(reg, sizes))
             return out
 
