@@ -52,9 +52,14 @@ def _compile(name, verbose):
 
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "flags.txt")
+    flags_now = " ".join([NVCC, *ARCH, *FLAGS])
+    if not os.path.exists(stamp) or open(stamp).read() != flags_now:
+        force = True  # objects compiled with other flags (e.g. before gemm_tc.cu existed) are stale
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
+    open(stamp, "w").write(flags_now)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         res = list(ex.map(lambda s: _compile(s, verbose), srcs))

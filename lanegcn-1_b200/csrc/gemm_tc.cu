@@ -2,10 +2,13 @@
 //
 //   out[m, ob*128 + c] = epi( sum_s A_s[idx_s[m], :] . W[ob*128 + c, s*128:(s+1)*128] )      fp32 in, fp32 out
 //
-// Precision: 3xTF32.  Every fp32 operand x is split into hi = tf32(x) (round-to-nearest) and lo = x - hi
-// (exact in fp32, then truncated to tf32 by the tensor core); the product is accumulated in fp32 in TMEM as
-//   D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi
-// which keeps ~21 mantissa bits — inside the 1e-4 / 1e-5 budget where plain TF32 is not.
+// Precision: 3xTF32.  Every fp32 operand x is split into hi = tf32(x) and lo = tf32(x - hi) (both rounded to
+// nearest), and   D = sum A_hi.B_hi  +  sum (A_lo.B_hi + A_hi.B_lo)   is accumulated in fp32 in TMEM — in TWO
+// accumulators.  Measured on B200 (tools/error_budget.py): the tensor core truncates toward zero once per MMA
+// instruction (about -1.3e-8 relative per instruction), so folding the 32 cross-term instructions into the
+// main accumulator triples its bias; a separate cross accumulator (2^-11 smaller, so its own truncation is
+// negligible) is added in the epilogue with one IEEE fp32 add.  Result: ~21 mantissa bits, inside the
+// 1e-4 / 1e-5 budget where plain TF32 is not.
 //
 // Structure (one persistent CTA per SM, 288 threads, warp-specialised):
 //   warps 0-3  producers.  Load the 128-row A tile (optionally row-gathered) with coalesced 128-bit loads,
@@ -15,12 +18,13 @@
 //              stream the weight tile of each output block the same way, one 32-float K-chunk per pipeline
 //              stage (hi+lo = 32 KB/stage, 2 stages).
 //   warp 8     MMA issuer (one elected lane): per stage 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=128,
-//              K=8), accumulator in TMEM (2 x 128 columns: double-buffered so the epilogue of tile i overlaps
-//              the MMAs of tile i+1); tcgen05.commit hands smem stages back and publishes accumulators.
+//              K=8), accumulators in TMEM (2 stages x [main 128 | cross 128] columns: double-buffered so the
+//              epilogue of tile i overlaps the MMAs of tile i+1); tcgen05.commit hands smem stages back and
+//              publishes accumulators.
 //   warps 4-7  epilogue.  tcgen05.ld the accumulator row (thread == row, so GroupNorm(1) statistics are
 //              thread-local), apply GN / ReLU / residual / ReLU, stage 32x32 fp32 blocks in swizzled smem and
 //              write them with TMA bulk tensor stores (coalesced 128 B rows, M-tail clipped by the tensor map).
-// Shared memory: A hi+lo 128 KB | B 2 x 32 KB | store staging 32 KB | barriers.  TMEM: 256 columns.
+// Shared memory: A hi+lo 128 KB | B 2 x 32 KB | store staging 32 KB | barriers.  TMEM: all 512 columns.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -38,7 +42,7 @@ constexpr int kSmemBar = kSmemOut + 4 * 2 * 4096;   // 224 KB
 constexpr int kSmemTotal = kSmemBar + 256;
 constexpr int kSmemAlloc = kSmemTotal + 1024;       // slack for manual 1024-byte alignment
 constexpr int kNumThreads = 288;
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;   // 2 stages x (main + cross accumulator) x 128 columns
 // instruction descriptor, kind::tf32: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major,
 // N=128 (16<<17), M=128 (8<<24)                                            (cute/arch/mma_sm100_desc.hpp:412)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
@@ -99,15 +103,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         "=r"(v[base + 30]), "=r"(v[base + 31])                                                                \
       : "r"(taddr))
 
-// hi = tf32(x) rounded to nearest (ties away), lo = x - hi.  16-byte stores at the SWIZZLE_128B position of
+// hi = tf32(x), lo = tf32(x - hi), both rounded to nearest (ties away).  16-byte stores at the SWIZZLE_128B position of
 // (row, 16-byte chunk c) inside a [rows][128 B] K-chunk block: chunk index XOR (row & 7).
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  return __uint_as_float(t);
+}
 __device__ __forceinline__ void split_store(uint8_t* hi_blk, uint8_t* lo_blk, int row, int c, float4 x) {
   float4 h, l;
   uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t); l.x = x.x - h.x;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t); l.y = x.y - h.y;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t); l.z = x.z - h.z;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t); l.w = x.w - h.w;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t); l.x = tf32_rna(x.x - h.x);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t); l.y = tf32_rna(x.y - h.y);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t); l.z = tf32_rna(x.z - h.z);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t); l.w = tf32_rna(x.w - h.w);
   const int off = row * 128 + ((c ^ (row & 7)) << 4);
   *reinterpret_cast<float4*>(hi_blk + off) = h;
   *reinterpret_cast<float4*>(lo_blk + off) = l;
@@ -227,7 +236,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
           if (s == 0) {  // a fresh accumulator: wait until the epilogue has drained this TMEM stage
             mbar_wait(bar_acc_empty + 8 * acc_stage, acc_phase ^ 1);
           }
-          const uint32_t d_tmem = tmem_base + acc_stage * 128;
+          const uint32_t d_main = tmem_base + acc_stage * 256, d_cross = d_main + 128;
           for (int kc = 0; kc < 4; ++kc) {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             tc_fence_after();
@@ -237,9 +246,9 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {  // K = 8 floats = 32 bytes per instruction
                 const uint32_t first = (s == 0 && kc == 0 && j == 0) ? 0u : 1u;
-                umma_tf32(d_tmem, umma_desc(a_lo + 32 * j), umma_desc(b_hi + 32 * j), first);
-                umma_tf32(d_tmem, umma_desc(a_hi + 32 * j), umma_desc(b_lo + 32 * j), 1u);
-                umma_tf32(d_tmem, umma_desc(a_hi + 32 * j), umma_desc(b_hi + 32 * j), 1u);
+                umma_tf32(d_cross, umma_desc(a_lo + 32 * j), umma_desc(b_hi + 32 * j), first);
+                umma_tf32(d_cross, umma_desc(a_hi + 32 * j), umma_desc(b_lo + 32 * j), 1u);
+                umma_tf32(d_main, umma_desc(a_hi + 32 * j), umma_desc(b_hi + 32 * j), first);
               }
               umma_commit(bar_b_empty + 8 * b_stage);  // smem stage reusable once these MMAs retire
               if (kc == 3 && s == a.n_src - 1) umma_commit(bar_acc_full + 8 * acc_stage);
@@ -274,12 +283,20 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
         mbar_wait(bar_acc_full + 8 * acc_stage, acc_phase);
         tc_fence_after();
         uint32_t v[128];
-        const uint32_t taddr = tmem_base + acc_stage * 128 + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + acc_stage * 256 + ((uint32_t)(q * 32) << 16);
         TMEM_LD32(v, 0, taddr);
         TMEM_LD32(v, 32, taddr + 32);
         TMEM_LD32(v, 64, taddr + 64);
         TMEM_LD32(v, 96, taddr + 96);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {  // + cross-term accumulator (columns 128..255 of the stage)
+          uint32_t x[32];
+          TMEM_LD32(x, 0, taddr + 128 + cb * 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[cb * 32 + c] = __float_as_uint(__uint_as_float(v[cb * 32 + c]) + __uint_as_float(x[c]));
+        }
         tc_fence_before();
         mbar_arrive(bar_acc_empty + 8 * acc_stage);  // TMEM stage may be overwritten by the next MMAs
         if (++acc_stage == 2) {
