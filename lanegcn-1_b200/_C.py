@@ -24,6 +24,7 @@ _SIGS = {
     "lgcn_last_error": (C.c_char_p, []),
     "lgcn_get_gemm_engine": (_i32, []),
     "lgcn_set_gemm_engine": (_i32, [_i32]),
+    "lgcn_debug_flags": (_i32, [_i32]),
     "lgcn_launch_count": (_i64, []),
     "lgcn_prof_enable": (_i32, [_i32]),
     "lgcn_prof_collect": (_i32, [_vp, _vp]),

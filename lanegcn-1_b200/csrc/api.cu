@@ -54,6 +54,13 @@ extern "C" int lgcn_prof_collect(double* ms_by_kind, int64_t* launches_by_kind) 
   return 0;
 }
 static int g_engine = -1;  // -1: not decided yet
+static int g_debug = 0;
+int lgcn_debug_get() { return g_debug; }
+extern "C" int lgcn_debug_flags(int flags) {
+  const int prev = g_debug;
+  g_debug = flags;
+  return prev;
+}
 
 void lgcn_set_error(const char* fmt, ...) {
   va_list ap;
@@ -108,6 +115,7 @@ extern "C" int lgcn_linear128(const float* a0, const int32_t* idx0, const float*
   a.idx[0] = idx0; a.idx[1] = idx1; a.idx[2] = idx2;
   a.n_src = n_src; a.xs = xs; a.ks = ks; a.W = W; a.n_out_blocks = n_out_blocks;
   a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = ldo; a.m = m;
+  a.dbg = g_debug;
   if (check_linear(a)) return -1;
   return lgcn_launch_linear(a, (cudaStream_t)stream);
 }
@@ -118,6 +126,7 @@ static LinearArgs lin1(const float* x, const int32_t* idx, const float* W, const
   memset(&a, 0, sizeof(a));
   a.a[0] = x; a.idx[0] = idx; a.n_src = 1; a.W = W; a.n_out_blocks = 1;
   a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = LGCN_C; a.m = m;
+  a.dbg = g_debug;
   return a;
 }
 

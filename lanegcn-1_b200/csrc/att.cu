@@ -65,46 +65,89 @@ k_pairs(const float2* __restrict__ agt_ctrs, const float2* __restrict__ ctx_ctrs
   if (!FILL && lane == 0) cnt[r] = run;
 }
 
-// Single CTA: per-scene totals from the scanned counts, then the reference's offset bookkeeping
-// (lanegcn.py:681-687: a scene without pairs `continue`s BEFORE hi_count/wi_count advance), then the
-// destination-indexed rowptr.  ws layout (int32): row_start[n_agt+1] | hi_off[B] | wi_off[B] | cnt[n_agt]
+// Per-scene totals from the scanned counts, then the reference's offset bookkeeping (lanegcn.py:681-687: a scene
+// without pairs `continue`s BEFORE hi_count/wi_count advance).  One CTA: thread b owns scene b, the two running
+// offsets are block-wide exclusive scans of the sizes of the scenes that have pairs.
+// ws layout (int32): row_start[n_agt+1] | hi_off[B] | wi_off[B] | cnt[n_agt] | scan scratch[1088]
 __global__ void __launch_bounds__(1024)
-k_pairs_offsets(const int32_t* __restrict__ row_start, const int32_t* __restrict__ agt_off,
-                const int32_t* __restrict__ ctx_off, int n_scenes, int64_t n_agt, int keep_quirk,
-                int32_t* __restrict__ hi_off, int32_t* __restrict__ wi_off, int32_t* __restrict__ rowptr_dst) {
-  __shared__ int32_t used_rows;
-  const int32_t P = row_start[n_agt];
-  if (threadIdx.x == 0) {
-    int32_t hc = 0, wc = 0;
-    for (int b = 0; b < n_scenes; ++b) {
+k_pairs_scene_offsets(const int32_t* __restrict__ row_start, const int32_t* __restrict__ agt_off,
+                      const int32_t* __restrict__ ctx_off, int n_scenes, int keep_quirk,
+                      int32_t* __restrict__ hi_off, int32_t* __restrict__ wi_off, int32_t* __restrict__ used_rows) {
+  __shared__ int32_t wt[32];
+  __shared__ int32_t carry[2];
+  if (threadIdx.x == 0) carry[0] = carry[1] = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n_scenes; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    int32_t na = 0, nc = 0;
+    if (b < n_scenes) {
       const int32_t tot = row_start[agt_off[b + 1]] - row_start[agt_off[b]];
-      if (keep_quirk) {
-        hi_off[b] = hc;
-        wi_off[b] = wc;
-        if (tot > 0) {
-          hc += agt_off[b + 1] - agt_off[b];
-          wc += ctx_off[b + 1] - ctx_off[b];
+      if (!keep_quirk || tot > 0) {
+        na = agt_off[b + 1] - agt_off[b];
+        nc = ctx_off[b + 1] - ctx_off[b];
+      }
+    }
+    // two block-wide inclusive scans (warp shuffles + one smem hop)
+    int32_t inc[2] = {na, nc};
+    for (int k = 0; k < 2; ++k) {
+      int32_t v = inc[k];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += u;
+      }
+      if ((threadIdx.x & 31) == 31) wt[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        int32_t x = wt[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t u = __shfl_up_sync(0xffffffffu, x, o);
+          if (threadIdx.x >= o) x += u;
         }
+        wt[threadIdx.x] = x;
+      }
+      __syncthreads();
+      inc[k] = v + ((threadIdx.x >> 5) ? wt[(threadIdx.x >> 5) - 1] : 0) + carry[k];
+      __syncthreads();
+    }
+    if (b < n_scenes) {
+      if (keep_quirk) {
+        hi_off[b] = inc[0] - na;
+        wi_off[b] = inc[1] - nc;
       } else {
         hi_off[b] = agt_off[b];
         wi_off[b] = ctx_off[b];
-        hc = agt_off[b + 1];
       }
     }
-    used_rows = hc;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+      carry[0] = inc[0];
+      carry[1] = inc[1];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // destination row d = r - agt_off[b] + hi_off[b] for rows of scenes that have pairs (monotone, injective)
-  for (int64_t r = threadIdx.x; r < n_agt; r += blockDim.x) {
+  if (threadIdx.x == 0) *used_rows = keep_quirk ? carry[0] : agt_off[n_scenes];
+}
+
+// destination-indexed rowptr: d = r - agt_off[b] + hi_off[b] for rows of scenes that have pairs (monotone,
+// injective); rows past the last used destination point at P.
+__global__ void k_pairs_rowptr_dst(const int32_t* __restrict__ row_start, const int32_t* __restrict__ agt_off,
+                                   int n_scenes, int64_t n_agt, int keep_quirk, const int32_t* __restrict__ hi_off,
+                                   const int32_t* __restrict__ used_rows, int32_t* __restrict__ rowptr_dst) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_agt) return;
+  const int32_t P = row_start[n_agt];
+  if (r >= *used_rows) rowptr_dst[r] = P;  // includes r == n_agt
+  if (r < n_agt) {
     const int b = scene_of(agt_off, n_scenes, (int32_t)r);
     const int32_t tot = row_start[agt_off[b + 1]] - row_start[agt_off[b]];
     if (!keep_quirk || tot > 0) rowptr_dst[r - agt_off[b] + hi_off[b]] = row_start[r];
   }
-  for (int64_t d = used_rows + threadIdx.x; d <= n_agt; d += blockDim.x) rowptr_dst[d] = P;
 }
 
 static inline int64_t pairs_ws_ints(int64_t n_agt, int n_scenes) {
-  return lgcn_align_up(n_agt + 1, 64) + 2 * lgcn_align_up(n_scenes, 64) + lgcn_align_up(n_agt, 64);
+  return lgcn_align_up(n_agt + 1, 64) + 2 * lgcn_align_up(n_scenes, 64) + lgcn_align_up(n_agt, 64) + 1088;
 }
 
 extern "C" int64_t lgcn_pairs_workspace_bytes(int64_t n_agt, int n_scenes) {
@@ -127,9 +170,13 @@ extern "C" int lgcn_pairs_count(const float* agt_ctrs, const float* ctx_ctrs, co
         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     LGCN_LAUNCH_OK();
   }
-  if (lgcn_launch_exclusive_scan(cnt, row_start, n_agt, st)) return -2;
-  k_pairs_offsets<<<1, 1024, 0, st>>>(row_start, agt_off, ctx_off, n_scenes, n_agt, keep_quirk, hi_off, wi_off,
-                                      rowptr);
+  int32_t* scratch = cnt + lgcn_align_up(n_agt, 64);  // [0..1024] scan scratch, [1056] used_rows
+  if (lgcn_launch_exclusive_scan(cnt, row_start, n_agt, scratch, st)) return -2;
+  k_pairs_scene_offsets<<<1, 1024, 0, st>>>(row_start, agt_off, ctx_off, n_scenes, keep_quirk, hi_off, wi_off,
+                                            scratch + 1056);
+  LGCN_LAUNCH_OK();
+  k_pairs_rowptr_dst<<<lgcn_cdiv(n_agt + 1, 256), 256, 0, st>>>(row_start, agt_off, n_scenes, n_agt, keep_quirk, hi_off,
+                                                               scratch + 1056, rowptr);
   LGCN_LAUNCH_OK();
   if (h_total) {
     int32_t p = 0;

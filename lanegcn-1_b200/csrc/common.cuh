@@ -93,9 +93,11 @@ struct LinearArgs {
   float* out;
   int64_t ldo;
   int64_t m;
+  int dbg;  // ablation switches for profiling (lgcn_debug_flags); 0 in production
 };
+int lgcn_debug_get();
 int lgcn_launch_linear_simt(const LinearArgs& a, cudaStream_t st);
 int lgcn_launch_linear_tc(const LinearArgs& a, cudaStream_t st);  // tcgen05 3xTF32 (gemm_tc.cu)
 int lgcn_launch_linear(const LinearArgs& a, cudaStream_t st);     // engine dispatch
-// chunked single-CTA exclusive scan: out[0..n] (n+1 entries) from cnt[0..n)
-int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, cudaStream_t st);
+// exclusive scan: out[0..n] (n+1 entries) from cnt[0..n); scratch >= 1025 int32
+int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, int32_t* scratch, cudaStream_t st);

@@ -47,47 +47,99 @@ extern "C" int lgcn_pack_meta(const float* turn, const float* control, const flo
   return 0;
 }
 
-// ------------------------------------------------------------------ exclusive scan (single CTA, chunked)
-// n is at most a few hundred thousand rows; one CTA of 1024 threads, each owning a contiguous chunk,
-// needs a single block-level scan of the 1024 chunk sums.  ~10-20 us at n = 200k, launched a handful of
-// times per batch — not worth a decoupled look-back scan.
-__global__ void __launch_bounds__(1024) k_exclusive_scan(const int32_t* __restrict__ cnt,
-                                                         int32_t* __restrict__ out, int64_t n) {
-  __shared__ int32_t warp_tot[32];
-  const int t = threadIdx.x;
-  const int64_t chunk = (n + 1023) / 1024;
-  const int64_t beg = min(n, (int64_t)t * chunk), end = min(n, beg + chunk);
-  int32_t s = 0;
-  for (int64_t i = beg; i < end; ++i) s += cnt[i];
-  // inclusive scan of s across the block
-  int32_t v = s;
+// ------------------------------------------------------------------ exclusive scan
+// n is at most a few hundred thousand rows.  Three tiny launches: (1) per-block sums of 4096-element chunks,
+// (2) one block scans the <= 1024 chunk sums, (3) every block scans its chunk with its base.  All loads are
+// the array is at most ~1 MB, i.e. L2-resident between the passes.
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 16  // per thread -> 4096 elements per block
+
+__device__ __forceinline__ int32_t block_inclusive_scan(int32_t v, int32_t* warp_tot /* [32] */, int32_t* total) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int32_t u = __shfl_up_sync(0xffffffffu, v, o);
-    if ((t & 31) >= o) v += u;
+    const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
   }
-  if ((t & 31) == 31) warp_tot[t >> 5] = v;
+  if (lane == 31) warp_tot[w] = v;
   __syncthreads();
-  if (t < 32) {
-    int32_t w = warp_tot[t];
+  if (w == 0) {
+    int32_t x = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int32_t u = __shfl_up_sync(0xffffffffu, w, o);
-      if (t >= o) w += u;
+      const int32_t u = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += u;
     }
-    warp_tot[t] = w;
+    warp_tot[lane] = x;
   }
   __syncthreads();
-  int32_t run = v - s + ((t >> 5) ? warp_tot[(t >> 5) - 1] : 0);  // exclusive prefix of this chunk
-  for (int64_t i = beg; i < end; ++i) {
-    out[i] = run;
-    run += cnt[i];
-  }
-  if (t == 1023) out[n] = warp_tot[31];
+  if (total) *total = warp_tot[(blockDim.x >> 5) - 1];
+  const int32_t r = v + (w ? warp_tot[w - 1] : 0);
+  __syncthreads();
+  return r;
 }
 
-int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, cudaStream_t st) {
-  k_exclusive_scan<<<1, 1024, 0, st>>>(cnt, out, n);
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block_sums(const int32_t* __restrict__ cnt, int32_t* __restrict__ sums, int64_t n) {
+  __shared__ int32_t wt[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS;
+  int32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t j = base + (int64_t)i * SCAN_BLOCK + threadIdx.x;
+    if (j < n) s += cnt[j];
+  }
+  int32_t total;
+  block_inclusive_scan(s, wt, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ sums, int nb, int32_t* __restrict__ out_total) {
+  __shared__ int32_t wt[32];
+  const int32_t v = threadIdx.x < nb ? sums[threadIdx.x] : 0;
+  int32_t total;
+  const int32_t inc = block_inclusive_scan(v, wt, &total);
+  if (threadIdx.x < nb) sums[threadIdx.x] = inc - v;  // exclusive base of each chunk
+  if (threadIdx.x == 0) *out_total = total;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const int32_t* __restrict__ cnt, const int32_t* __restrict__ sums,
+                                                           int32_t* __restrict__ out, int64_t n) {
+  __shared__ int32_t wt[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS;
+  int32_t run = sums[blockIdx.x];
+  // thread t owns SCAN_ITEMS CONSECUTIVE elements (strided reads hit L2: the array is at most ~1 MB)
+  int32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t j = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+    v[i] = j < n ? cnt[j] : 0;
+    s += v[i];
+  }
+  const int32_t inc = block_inclusive_scan(s, wt, nullptr);
+  run += inc - s;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t j = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+    if (j < n) out[j] = run;
+    run += v[i];
+  }
+}
+
+// out[0..n] (n+1 entries, out[n] = total).  `scratch` (>= 1025 int32, caller-provided so the call stays
+// re-entrant) holds the chunk sums.
+int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, int32_t* scratch, cudaStream_t st) {
+  const int64_t per = (int64_t)SCAN_BLOCK * SCAN_ITEMS;
+  const int64_t nb = (n + per - 1) / per;
+  LGCN_CHECK_ARG(nb <= 1024, "exclusive_scan: %lld elements exceed the 4M-element limit", (long long)n);
+  if (nb == 0) {
+    LGCN_CUDA_OK(cudaMemsetAsync(out, 0, 4, st));
+    return 0;
+  }
+  k_scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, n);
+  LGCN_LAUNCH_OK();
+  k_scan_sums<<<1, 1024, 0, st>>>(scratch, (int)nb, out + n);
+  LGCN_LAUNCH_OK();
+  k_scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, out, n);
   LGCN_LAUNCH_OK();
   return 0;
 }
@@ -159,8 +211,8 @@ __global__ void k_csr_finish(EdgeSets es, int64_t n_nodes, const int32_t* __rest
 }
 
 extern "C" int64_t lgcn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
-  // cnt/cursor int32[n_nodes] + slot_edge int32[n_edges]
-  return lgcn_align_up(4 * n_nodes, 256) + lgcn_align_up(4 * n_edges, 256) + 256;
+  // cnt/cursor int32[n_nodes] + slot_edge int32[n_edges] + scan scratch int32[1025]
+  return lgcn_align_up(4 * n_nodes, 256) + lgcn_align_up(4 * n_edges, 256) + 4352 + 256;
 }
 
 extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len,
@@ -183,6 +235,7 @@ extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h
   LGCN_CHECK_ARG(n_nodes * (int64_t)(n_keys + 1) < (int64_t)1 << 31, "csr_build: block index exceeds int32");
   int32_t* cnt = (int32_t*)workspace;
   int32_t* slot_edge = (int32_t*)((char*)workspace + lgcn_align_up(4 * n_nodes, 256));
+  int32_t* scan_scratch = (int32_t*)((char*)slot_edge + lgcn_align_up(4 * E, 256));
   LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_nodes, st));
   LGCN_CUDA_OK(cudaMemsetAsync(err_flag, 0, 4, st));
   const unsigned eb = E ? min(lgcn_cdiv(E, 256), 148u * 16u) : 0u;
@@ -190,7 +243,7 @@ extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h
     k_csr_hist<<<eb, 256, 0, st>>>(es, n_nodes, cnt, err_flag);
     LGCN_LAUNCH_OK();
   }
-  if (lgcn_launch_exclusive_scan(cnt, rowptr, n_nodes, st)) return -2;
+  if (lgcn_launch_exclusive_scan(cnt, rowptr, n_nodes, scan_scratch, st)) return -2;
   if (eb) {
     LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_nodes, st));
     k_csr_place<<<eb, 256, 0, st>>>(es, n_nodes, rowptr, cnt, slot_edge);

@@ -79,6 +79,16 @@ class _Workspace:
         return buf
 
 
+_SIDE_STREAMS: Dict = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _need_cuda(t: Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"lanegcn_b200: {what} must be a CUDA tensor (there is no CPU path)")
@@ -676,8 +686,15 @@ class Net(nn.Module):
                 (actor_ctrs, node_ctrs, cfg["map2actor_dist"]),
                 (actor_ctrs, actor_ctrs, cfg["actor2actor_dist"]),
             ])
-            actors = self.actor_net(b.actors.transpose(1, 2).contiguous())        # :129-131
+            # ActorNet (stock PyTorch, many tiny launches) does not depend on the map: run it on a side stream
+            # so it overlaps the MapNet kernels, and join before A2M needs the actor features.
+            cur, side = torch.cuda.current_stream(), _side_stream(b.actors.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                actors = self.actor_net(b.actors.transpose(1, 2).contiguous())    # :129-131
             nodes, node_idcs, node_ctrs = self.map_net(graph)                     # :135
+            cur.wait_stream(side)
+            actors.record_stream(cur)
             nodes = self.a2m(nodes, graph, actors, actor_idcs, actor_ctrs, pairs=p_a2m)   # :138
             nodes = self.m2m(nodes, graph)                                        # :139
             actors = self.m2a(actors, actor_idcs, actor_ctrs, nodes, node_idcs, node_ctrs, pairs=p_m2a)  # :140
