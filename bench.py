@@ -163,9 +163,11 @@ def run_ours(args):
     net.load_state_dict(synth.seeded_state_dict(shapes, 0))
     net = net.to(dev).eval()
 
+    plan = shard.make_plan([len(s["ctrs"]) for s in scenes]) if world > 1 else None  # host metadata, once per batch
+
     def step_device(staged):
         out = net.forward_device(staged)
-        return shard.gather_outputs(out) if world > 1 else out
+        return shard.gather_outputs(out, plan) if world > 1 else out
 
     def sync_all():
         torch.cuda.synchronize()
@@ -213,7 +215,7 @@ def run_ours(args):
     def step_e2e():
         out = net(data)
         if world > 1:
-            out = shard.gather_outputs(out)
+            out = shard.gather_outputs(out, shard.make_plan([len(c) for c in data["ctrs"]]))
         return torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
 
     for _ in range(3):

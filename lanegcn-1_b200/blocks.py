@@ -133,11 +133,16 @@ class PredNet(nn.Module):
 
     def forward(self, actors, actor_idcs, actor_ctrs):
         ctrs = actor_ctrs.cat if hasattr(actor_ctrs, "cat") else torch.cat(list(actor_ctrs), 0)
+        cls, reg = self.core(actors, ctrs)
+        sizes = [len(i) for i in actor_idcs]
+        return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
+
+    def core(self, actors, ctrs):
+        """Per-actor part (no host-side sizes): actors [A,n], ctrs [A,2] -> cls [A,K], reg [A,K,T,2]."""
         reg = torch.stack([head(actors) for head in self.pred], 1)
         reg = reg.view(reg.size(0), reg.size(1), -1, 2) + ctrs.view(-1, 1, 1, 2)
         feats = self.att_dest(actors, ctrs, reg[:, :, -1].detach())
         cls = self.cls(feats).view(-1, self.num_mods)
         cls, order = cls.sort(1, descending=True)
         reg = torch.gather(reg, 1, order.view(-1, self.num_mods, 1, 1).expand(-1, -1, reg.size(2), 2))
-        sizes = [len(i) for i in actor_idcs]
-        return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
+        return cls, reg

@@ -13,6 +13,7 @@ There is no CPU path: tensors must live on a CUDA device and the library must be
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -234,7 +235,7 @@ def stage_graphs(graphs: List[dict]) -> StagedGraphs:
     parts = []
     for key in ("ctrs", "feats", "turn", "control", "intersect"):
         parts += [g[key].reshape(-1) for g in graphs]
-    sg.fl = _stage(torch.cat(parts), dev, torch.float32)
+    sg.fl = _stage_cat(parts, dev, torch.float32, "graph_fl")
     locs, seg_add = [], []
     for k1, s in _edge_names(sg.num_scales):
         for k2 in ("u", "v"):
@@ -250,12 +251,12 @@ def stage_graphs(graphs: List[dict]) -> StagedGraphs:
         dt, locs = torch.int64, [t.long() for t in locs]
     if dt not in (torch.int16, torch.int32, torch.int64):
         raise RuntimeError(f"lanegcn_b200: edge indices must be int16/int32/int64, got {dt}")
-    sg.local = _stage(torch.cat(locs), dev, dt)
+    sg.local = _stage_cat(locs, dev, dt, "graph_idx")
     seg_start = [0]
     for n in sg.seg_len:
         seg_start.append(seg_start[-1] + n)
-    sg.segs = _stage(torch.tensor(seg_start + seg_add, dtype=torch.int64), dev, torch.int64)
-    sg.off_dev = _stage(torch.tensor(sg.off, dtype=torch.int32), dev, torch.int32)
+    sg.segs = _stage(torch.tensor(seg_start + seg_add, dtype=torch.int64), dev, torch.int64, "segs")
+    sg.off_dev = _stage(torch.tensor(sg.off, dtype=torch.int32), dev, torch.int32, "off")
     sg.h2d_bytes = sum(t.numel() * t.element_size() for t in (sg.fl, sg.local, sg.segs, sg.off_dev))
     return sg
 
@@ -314,13 +315,49 @@ def _target_device(t: Tensor):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _stage(t: Tensor, dev, dtype) -> Tensor:
+class _PinnedPool:
+    """Reusable page-locked staging buffers (cudaHostAlloc costs milliseconds, so never per batch).  A slot is
+    reused only after the async H2D copy that last read it has completed (event per slot)."""
+
+    _slots: Dict = {}
+    RING = 3
+
+    @classmethod
+    def take(cls, tag: str, nbytes: int):
+        ring = cls._slots.setdefault(tag, {"i": 0, "bufs": [None] * cls.RING, "evs": [None] * cls.RING})
+        i = ring["i"] = (ring["i"] + 1) % cls.RING
+        if ring["evs"][i] is not None:
+            ring["evs"][i].synchronize()
+        buf = ring["bufs"][i]
+        if buf is None or buf.numel() < nbytes:
+            buf = ring["bufs"][i] = torch.empty(max(int(nbytes * 1.5), 4096), dtype=torch.uint8).pin_memory()
+        return ring, i, buf
+
+
+def _stage_cat(parts: List[Tensor], dev, dtype, tag: str) -> Tensor:
+    """Concatenate 1-D CPU tensors straight into a pinned buffer and issue ONE async H2D copy.
+    Device inputs are concatenated on the device."""
+    if parts[0].is_cuda:
+        return torch.cat([p.to(dtype) for p in parts])
+    n = sum(p.numel() for p in parts)
+    esz = torch.empty(0, dtype=dtype).element_size()
+    ring, i, buf = _PinnedPool.take(tag, n * esz)
+    host = buf[: n * esz].view(dtype)
+    if n:
+        torch.cat(parts, out=host) if all(p.dtype == dtype for p in parts) else torch.cat([p.to(dtype) for p in parts], out=host)
+    out = host.to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    ring["evs"][i] = ev
+    return out
+
+
+def _stage(t: Tensor, dev, dtype, tag: str = "misc") -> Tensor:
     """CPU tensor -> pinned -> device with one async copy; device tensors pass through."""
-    if t.dtype != dtype:
-        t = t.to(dtype)
     if t.is_cuda:
-        return t.contiguous()
-    return t.contiguous().pin_memory().to(dev, non_blocking=True)
+        return t.to(dtype).contiguous()
+    shape = t.shape
+    return _stage_cat([t.reshape(-1)], dev, dtype, tag + str(dtype)).view(shape)
 
 
 # --------------------------------------------------------------------------- Att pair lists
@@ -615,6 +652,45 @@ class A2A(nn.Module):
         return actors
 
 
+# --------------------------------------------------------------------------- CUDA graphs for the stock-PyTorch nets
+class _Graphed:
+    """Replays a row-independent stock-PyTorch function (ActorNet, PredNet core) as ONE CUDA-graph launch.
+    Those nets are ~100 tiny kernels each: off the hot path, but their launch cost on the host dominates a
+    step once the graph kernels are fast (and it does not shrink when scenes are sharded over more GPUs).
+    Rows (actors) are independent, so the row count is padded up to a bucket and one graph per bucket is
+    captured; weights are read through their parameter storage, so in-place updates / load_state_dict are seen."""
+
+    BUCKET = 64
+
+    def __init__(self, fn):
+        self.fn, self.cache = fn, {}
+
+    def __call__(self, *inputs: Tensor):
+        n = inputs[0].shape[0]
+        npad = max(self.BUCKET, (n + self.BUCKET - 1) // self.BUCKET * self.BUCKET)
+        key = (npad, str(inputs[0].device)) + tuple(tuple(x.shape[1:]) for x in inputs)
+        ent = self.cache.get(key)
+        if ent is None:
+            static_in = [torch.zeros((npad,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device) for x in inputs]
+            warm = torch.cuda.Stream(device=inputs[0].device)
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                for _ in range(2):
+                    self.fn(*static_in)
+            torch.cuda.current_stream().wait_stream(warm)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self.fn(*static_in)
+            ent = self.cache[key] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        for dst, src in zip(static_in, inputs):
+            dst[:n].copy_(src, non_blocking=True)
+        g.replay()
+        if isinstance(static_out, tuple):
+            return tuple(o[:n] for o in static_out)
+        return static_out[:n]
+
+
 # --------------------------------------------------------------------------- Net
 class DeviceBatch:
     """A collated batch after its host->device copies and before any kernel: the input of
@@ -626,7 +702,8 @@ class DeviceBatch:
         self.graphs = None       # StagedGraphs
         self.rot = None          # f32 [B,2,2]
         self.orig = None         # f32 [B,2]
-        self.scene_of_actor = None  # int64 [sum A]
+        self.rot_a = None        # f32 [sum A,2,2]  the scene's rot, per actor
+        self.orig_a = None       # f32 [sum A,2]
         self.h2d_bytes = 0
 
 
@@ -643,6 +720,14 @@ class Net(nn.Module):
         self.m2a = M2A(config)
         self.a2a = A2A(config)
         self.pred_net = PredNet(config)
+        self.use_cuda_graphs = os.environ.get("LGCN_NO_GRAPHS", "0") != "1"  # ActorNet / PredNet only
+        self._g_actor = _Graphed(self.actor_net)
+        self._g_pred = _Graphed(self._pred_core)
+
+    def _pred_core(self, actors, ctrs, rot_a, orig_a):
+        """PredNet + the world transform of lanegcn.py:145-150, per actor row (graph-capturable)."""
+        cls, reg = self.pred_net.core(actors, ctrs)
+        return cls, torch.matmul(reg, rot_a.unsqueeze(1)) + orig_a.view(-1, 1, 1, 2)
 
     def _device(self):
         dev = next(self.parameters()).device
@@ -656,15 +741,15 @@ class Net(nn.Module):
         with torch.cuda.device(dev):
             b = DeviceBatch()
             sizes = [len(x) for x in data["feats"]]
-            b.actors = _stage(torch.cat(list(data["feats"]), 0), dev, torch.float32)
-            b.actor_ctrs = scene_list(_stage(torch.cat(list(data["ctrs"]), 0), dev, torch.float32), sizes)
-            b.rot = _stage(torch.stack(list(data["rot"])), dev, torch.float32)
-            b.orig = _stage(torch.stack(list(data["orig"])), dev, torch.float32)
-            b.scene_of_actor = _stage(torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes)), dev,
-                                      torch.int64)
+            b.actors = _stage(torch.cat(list(data["feats"]), 0), dev, torch.float32, "actors")
+            b.actor_ctrs = scene_list(_stage(torch.cat(list(data["ctrs"]), 0), dev, torch.float32, "actr"), sizes)
+            b.rot = _stage(torch.stack(list(data["rot"])), dev, torch.float32, "rot")
+            b.orig = _stage(torch.stack(list(data["orig"])), dev, torch.float32, "orig")
+            b.rot_a = torch.repeat_interleave(b.rot, torch.tensor(sizes, device=dev), 0, output_size=sum(sizes))
+            b.orig_a = torch.repeat_interleave(b.orig, torch.tensor(sizes, device=dev), 0, output_size=sum(sizes))
             b.graphs = stage_graphs(data["graph"])
             b.h2d_bytes = b.graphs.h2d_bytes + 4 * (b.actors.numel() + b.actor_ctrs.cat.numel() + b.rot.numel()
-                                                    + b.orig.numel()) + 4 * (len(sizes) + 1) + 8 * b.scene_of_actor.numel()
+                                                    + b.orig.numel()) + 12 * (len(sizes) + 1)
             return b
 
     @torch.no_grad()
@@ -686,25 +771,27 @@ class Net(nn.Module):
                 (actor_ctrs, node_ctrs, cfg["map2actor_dist"]),
                 (actor_ctrs, actor_ctrs, cfg["actor2actor_dist"]),
             ])
-            # ActorNet (stock PyTorch, many tiny launches) does not depend on the map: run it on a side stream
-            # so it overlaps the MapNet kernels, and join before A2M needs the actor features.
+            # MapNet is a handful of C-ABI calls: enqueue it FIRST so the GPU is busy while the host launches
+            # ActorNet (stock PyTorch; independent of the map) on a side stream; join before A2M.
             cur, side = torch.cuda.current_stream(), _side_stream(b.actors.device)
             side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                actors = self.actor_net(b.actors.transpose(1, 2).contiguous())    # :129-131
             nodes, node_idcs, node_ctrs = self.map_net(graph)                     # :135
+            with torch.cuda.stream(side):
+                x = b.actors.transpose(1, 2).contiguous()
+                actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
             cur.wait_stream(side)
             actors.record_stream(cur)
             nodes = self.a2m(nodes, graph, actors, actor_idcs, actor_ctrs, pairs=p_a2m)   # :138
             nodes = self.m2m(nodes, graph)                                        # :139
             actors = self.m2a(actors, actor_idcs, actor_ctrs, nodes, node_idcs, node_ctrs, pairs=p_m2a)  # :140
             actors = self.a2a(actors, actor_idcs, actor_ctrs, pairs=p_a2a)        # :141
-            out = self.pred_net(actors, actor_idcs, actor_ctrs)                   # :144
-            # world transform (lanegcn.py:145-150), batched: every actor uses its scene's rot/orig
-            reg = torch.cat(out["reg"], 0)
-            reg = torch.matmul(reg, b.rot[b.scene_of_actor].unsqueeze(1)) + b.orig[b.scene_of_actor].view(-1, 1, 1, 2)
-            out["reg"] = list(torch.split(reg, sizes))
-            return out
+            # PredNet + world transform (:144-150), batched over actors
+            if self.use_cuda_graphs:
+                cls, reg = self._g_pred(actors, actor_ctrs.cat, b.rot_a, b.orig_a)
+                cls, reg = cls.clone(), reg.clone()  # graph outputs are static buffers reused by the next replay
+            else:
+                cls, reg = self._pred_core(actors, actor_ctrs.cat, b.rot_a, b.orig_a)
+            return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
 
 
 def get_model():

@@ -37,42 +37,50 @@ def shard_batch(data: Dict[str, list], rank: int, world: int) -> Dict[str, list]
     return {k: v[r.start: r.stop] for k, v in data.items()}
 
 
-def gather_outputs(out: Dict[str, List[torch.Tensor]], group=None) -> Dict[str, List[torch.Tensor]]:
-    """All ranks receive every scene's ``cls``/``reg`` in global scene order.  One padded all_gather per
-    key (payload <= 1,464 B per actor), plus one tiny all_gather of the per-scene actor counts."""
+class GatherPlan:
+    """Who owns how many actors per scene, agreed once per batch (host metadata, no device work)."""
+
+    def __init__(self, per_rank: List[List[int]]):
+        self.per_rank = per_rank
+        self.max_actors = max(1, max(sum(s) for s in per_rank))
+
+
+def make_plan(local_sizes: Sequence[int], group=None) -> GatherPlan:
+    """One all_gather_object of the per-scene actor counts of every rank's shard (staging-time metadata: the
+    counts are known on the host before anything runs on the device)."""
     world = dist.get_world_size(group)
-    dev = out["cls"][0].device if out["cls"] else torch.device("cpu")
-    if len(out["cls"]) == 0 and dist.get_backend(group) == "nccl":
-        dev = torch.device("cuda", torch.cuda.current_device())
-    sizes = torch.tensor([len(x) for x in out["cls"]], dtype=torch.int64, device=dev)
-    n_scenes = torch.tensor([len(sizes)], dtype=torch.int64, device=dev)
-    all_n = [torch.zeros_like(n_scenes) for _ in range(world)]
-    dist.all_gather(all_n, n_scenes, group=group)
-    max_s = max(int(x) for x in all_n)
-    pad_sizes = torch.zeros(max(max_s, 1), dtype=torch.int64, device=dev)
-    pad_sizes[: len(sizes)] = sizes
-    all_sizes = [torch.zeros_like(pad_sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, pad_sizes, group=group)
-    per_rank = [s[: int(n)].tolist() for s, n in zip(all_sizes, all_n)]
-    max_a = max(1, max(sum(s) for s in per_rank))
-    res = {}
-    for key, tail in (("cls", (6,)), ("reg", (6, 30, 2))):
-        if out[key]:
-            tail = tuple(out[key][0].shape[1:])
-            mine = torch.cat(out[key], 0)
-        else:
-            mine = torch.zeros((0,) + tail, dtype=torch.float32, device=dev)
-        tail_t = torch.tensor(list(tail), dtype=torch.int64, device=dev)  # agree on the trailing shape
-        tails = [torch.zeros_like(tail_t) for _ in range(world)]
-        dist.all_gather(tails, tail_t, group=group)
-        tail = tuple(int(x) for x in max(tails, key=lambda t: int(t.prod())))
-        buf = torch.zeros((max_a,) + tail, dtype=torch.float32, device=dev)
-        if mine.numel():
-            buf[: mine.shape[0]] = mine
-        bufs = [torch.zeros_like(buf) for _ in range(world)]
-        dist.all_gather(bufs, buf, group=group)
-        scenes = []
-        for b, s in zip(bufs, per_rank):
-            scenes += list(torch.split(b[: sum(s)], s))
-        res[key] = scenes
+    per_rank: List = [None] * world
+    dist.all_gather_object(per_rank, [int(x) for x in local_sizes], group=group)
+    return GatherPlan(per_rank)
+
+
+def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, group=None) -> Dict[str, List[torch.Tensor]]:
+    """All ranks receive every scene's ``cls``/``reg`` in global scene order with ONE collective: cls [A,K] and
+    reg [A,K,T,2] are packed side by side into a [max_actors, K + K*T*2] buffer (1,464 B per actor in the
+    reference config) and all_gathered; no host synchronisation when ``plan`` is given."""
+    if plan is None:
+        plan = make_plan([len(x) for x in out["cls"]], group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = plan.per_rank[rank]
+    if out["cls"]:
+        cls, reg = torch.cat(out["cls"], 0), torch.cat(out["reg"], 0)
+        k, tail = cls.shape[1], tuple(reg.shape[1:])
+        dev = cls.device
+    else:  # a rank without scenes still takes part; shapes follow the reference config
+        k, tail = 6, (6, 30, 2)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        cls, reg = torch.zeros(0, k, device=dev), torch.zeros((0,) + tail, device=dev)
+    width = k + int(torch.tensor(tail).prod())
+    buf = torch.zeros(plan.max_actors, width, dtype=torch.float32, device=dev)
+    n = sum(mine)
+    if n:
+        buf[:n, :k] = cls
+        buf[:n, k:] = reg.reshape(n, -1)
+    full = torch.empty(world * plan.max_actors, width, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(full, buf, group=group)
+    res = {"cls": [], "reg": []}
+    for r, sizes in enumerate(plan.per_rank):
+        part = full[r * plan.max_actors: r * plan.max_actors + sum(sizes)]
+        res["cls"] += list(torch.split(part[:, :k], sizes))
+        res["reg"] += [x.reshape((-1,) + tail) for x in torch.split(part[:, k:], sizes)]
     return res
