@@ -41,7 +41,8 @@ int lgcn_set_gemm_engine(int engine);
 
 /* Profiling ablations of the tcgen05 GEMM (results become WRONG; never set in production; returns the previous
  * value): 1 = epilogue skips staging + TMA stores, 2 = epilogue skips the cross-accumulator reads,
- * 4 = MMA issuer skips the tcgen05.mma instructions, 8 = producers skip global loads and conversion. */
+ * 4 = MMA issuer skips the tcgen05.mma instructions, 8 = producers skip global loads and conversion,
+ * 16 = route the multi-block projection through the generic kernel instead of the A-in-TMEM one (results stay right). */
 int lgcn_debug_flags(int flags);
 /* number of CUDA kernels this library has launched in this process (all entry points) */
 int64_t lgcn_launch_count(void);

@@ -136,7 +136,9 @@ static LinearArgs lin1(const float* x, const int32_t* idx, const float* W, const
 extern "C" int64_t lgcn_laneconv_wpack_floats(int n_keys) { return (int64_t)(n_keys + 1) * CC + CC + 4 * LGCN_C; }
 
 extern "C" int64_t lgcn_laneconv_workspace_bytes(int64_t n_nodes, int n_keys) {
-  return lgcn_align_up(n_nodes * (int64_t)(n_keys + 1) * LGCN_C * 4, 1024) + lgcn_align_up(n_nodes * LGCN_C * 4, 1024) + 1024;
+  // Y [n, (K+1)*128] | h [n,128] | W_hi, W_lo [(K+1)*128, 128] (tf32 split of the current block's projection)
+  return lgcn_align_up(n_nodes * (int64_t)(n_keys + 1) * LGCN_C * 4, 1024) + lgcn_align_up(n_nodes * LGCN_C * 4, 1024) +
+         2 * lgcn_align_up((int64_t)(n_keys + 1) * CC * 4, 1024) + 1024;
 }
 
 extern "C" int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int32_t* col, int n_keys,
@@ -149,6 +151,13 @@ extern "C" int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int
   const int nb = n_keys + 1;
   float* Y = (float*)workspace;
   float* h = (float*)((char*)workspace + lgcn_align_up(n_nodes * (int64_t)nb * LGCN_C * 4, 1024));
+  float* w_hi = (float*)((char*)h + lgcn_align_up(n_nodes * LGCN_C * 4, 1024));
+  float* w_lo = (float*)((char*)w_hi + lgcn_align_up((int64_t)nb * CC * 4, 1024));
+#if LGCN_HAVE_TC
+  const bool wide_tc = lgcn_get_gemm_engine() == 1 && nb >= 2 && !(g_debug & 16);
+#else
+  const bool wide_tc = false;
+#endif
   for (int i = 0; i < n_blocks; ++i) {
     const float* w = wpack + (int64_t)i * lgcn_laneconv_wpack_floats(n_keys);
     const float* wctr2 = w + (int64_t)nb * CC;
@@ -160,7 +169,13 @@ extern "C" int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int
     LinearArgs wide = lin1(feat, nullptr, w, nullptr, nullptr, nullptr, 0, Y, n_nodes);
     wide.n_out_blocks = nb;
     wide.ldo = (int64_t)nb * LGCN_C;
-    {
+    if (wide_tc) {  // static weights: split into tf32 hi/lo once per block, then TMA feeds them to the tensor pipe
+#if LGCN_HAVE_TC
+      if (int rc = lgcn_split_tf32(w, w_hi, w_lo, (int64_t)nb * CC, st)) return rc;
+      LgcnProfScope ps(LGCN_PROF_WIDE, st);
+      if (int rc = lgcn_launch_wide_tc(wide, w_hi, w_lo, st)) return rc;
+#endif
+    } else {
       LgcnProfScope ps(LGCN_PROF_WIDE, st);
       if (int rc = lgcn_launch_linear(wide, st)) return rc;
     }

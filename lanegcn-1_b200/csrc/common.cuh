@@ -99,5 +99,8 @@ int lgcn_debug_get();
 int lgcn_launch_linear_simt(const LinearArgs& a, cudaStream_t st);
 int lgcn_launch_linear_tc(const LinearArgs& a, cudaStream_t st);  // tcgen05 3xTF32 (gemm_tc.cu)
 int lgcn_launch_linear(const LinearArgs& a, cudaStream_t st);     // engine dispatch
+// LaneConv wide projection on tcgen05 with the A tile in TMEM and TMA-fed pre-split weights (gemm_tc_wide.cu)
+int lgcn_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t st);
+int lgcn_launch_wide_tc(const LinearArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st);
 // exclusive scan: out[0..n] (n+1 entries) from cnt[0..n); scratch >= 1025 int32
 int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, int32_t* scratch, cudaStream_t st);

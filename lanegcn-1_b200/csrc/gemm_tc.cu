@@ -34,9 +34,9 @@
 //               Chan's formula through shared memory (two 64-thread named barriers).  Results are staged as
 //               32x32 fp32 blocks in swizzled shared memory and written with TMA bulk tensor stores (coalesced
 //               128 B rows; rows >= M clipped by the tensor map).
-#include <cuda.h>
+#include "tc_common.cuh"
 
-#include "common.cuh"
+using namespace tc;
 
 namespace {
 
@@ -53,100 +53,7 @@ constexpr int kSmemTotal = kSmemGamma + 1024;
 constexpr int kNumThreads = 416;
 constexpr int kMmaWarp = 12;
 constexpr uint32_t kTmemCols = 512;  // 2 stages x (main + cross accumulator) x 128 columns
-// instruction descriptor, kind::tf32: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major,
-// N=128 (16<<17), M=128 (8<<24)                                            (cute/arch/mma_sm100_desc.hpp:412)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded spin: a protocol bug must surface as a launch failure, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 28)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_shared_f2(uint32_t addr, float x, float y) {
-  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
-}
-__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp:91): start>>4 | LBO=1 |
-// SBO = 1024 B (8 rows x 128 B) | version 1 | layout SWIZZLE_128B (2)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-#define TMEM_LD32(v, base, taddr)                                                                             \
-  asm volatile(                                                                                               \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"  \
-      "%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                      \
-      : "=r"(v[base + 0]), "=r"(v[base + 1]), "=r"(v[base + 2]), "=r"(v[base + 3]), "=r"(v[base + 4]),        \
-        "=r"(v[base + 5]), "=r"(v[base + 6]), "=r"(v[base + 7]), "=r"(v[base + 8]), "=r"(v[base + 9]),        \
-        "=r"(v[base + 10]), "=r"(v[base + 11]), "=r"(v[base + 12]), "=r"(v[base + 13]), "=r"(v[base + 14]),   \
-        "=r"(v[base + 15]), "=r"(v[base + 16]), "=r"(v[base + 17]), "=r"(v[base + 18]), "=r"(v[base + 19]),   \
-        "=r"(v[base + 20]), "=r"(v[base + 21]), "=r"(v[base + 22]), "=r"(v[base + 23]), "=r"(v[base + 24]),   \
-        "=r"(v[base + 25]), "=r"(v[base + 26]), "=r"(v[base + 27]), "=r"(v[base + 28]), "=r"(v[base + 29]),   \
-        "=r"(v[base + 30]), "=r"(v[base + 31])                                                                \
-      : "r"(taddr))
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
-  return __uint_as_float(t);
-}
-// hi = tf32(x), lo = tf32(x - hi).  16-byte shared stores at the SWIZZLE_128B position of (row, 16-byte chunk c)
-// inside a [rows][128 B] K-chunk block: chunk index XOR (row & 7).
-__device__ __forceinline__ void split_store(uint32_t hi_blk, uint32_t lo_blk, int row, int c, float4 x) {
-  float4 h, l;
-  h.x = tf32_rna(x.x); l.x = tf32_rna(x.x - h.x);
-  h.y = tf32_rna(x.y); l.y = tf32_rna(x.y - h.y);
-  h.z = tf32_rna(x.z); l.z = tf32_rna(x.z - h.z);
-  h.w = tf32_rna(x.w); l.w = tf32_rna(x.w - h.w);
-  const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-  st_shared_f4(hi_blk + off, h);
-  st_shared_f4(lo_blk + off, l);
-}
+constexpr uint32_t kIdesc = idesc_tf32(128, 128);
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
@@ -300,9 +207,9 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t acc = (fresh && j == 0) ? 0u : 1u;
-        umma_tf32(d_cross, umma_desc(x_lo + 32 * j), umma_desc(w_hi + 32 * j), acc);
-        umma_tf32(d_cross, umma_desc(x_hi + 32 * j), umma_desc(w_lo + 32 * j), 1u);
-        umma_tf32(d_main, umma_desc(x_hi + 32 * j), umma_desc(w_hi + 32 * j), acc);
+        umma_tf32(d_cross, umma_desc(x_lo + 32 * j), umma_desc(w_hi + 32 * j), kIdesc, acc);
+        umma_tf32(d_cross, umma_desc(x_hi + 32 * j), umma_desc(w_lo + 32 * j), kIdesc, 1u);
+        umma_tf32(d_main, umma_desc(x_hi + 32 * j), umma_desc(w_hi + 32 * j), kIdesc, acc);
       }
     };
     auto next_stage = [&]() {
@@ -325,7 +232,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
         for (int kc = 0; kc < 4; ++kc) {
           mbar_wait(bar_b_full + 8 * b_stage, b_phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t w_hi = sbase + kSmemResHi + kc * kChunkBytes, w_lo = sbase + kSmemResLo + kc * kChunkBytes;
             const uint32_t x_hi = sbase + kSmemStream + b_stage * 2 * kChunkBytes, x_lo = x_hi + kChunkBytes;
             issue_stage(d_main, d_cross, x_hi, x_lo, w_hi, w_lo, kc == 0);
@@ -348,7 +255,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
             for (int kc = 0; kc < 4; ++kc) {
               mbar_wait(bar_b_full + 8 * b_stage, b_phase);
               tc_fence_after();
-              if (lane == 0) {
+              if (elect_one()) {
                 const uint32_t x_hi = sbase + kSmemResHi + kc * kChunkBytes, x_lo = sbase + kSmemResLo + kc * kChunkBytes;
                 const uint32_t w_hi = sbase + kSmemStream + b_stage * 2 * kChunkBytes, w_lo = w_hi + kChunkBytes;
                 issue_stage(d_main, d_cross, x_hi, x_lo, w_hi, w_lo, s == 0 && kc == 0);
@@ -420,7 +327,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
           }
         }
         // the staging buffer is reused every output block: the previous TMA store must have read it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         if (gn) {
           // GroupNorm(1 group) over 128 channels = two 64-channel halves held by two warps: local (mean, M2),
@@ -473,7 +380,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
             }
           }
           if (cb == 1) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
 #pragma unroll
@@ -484,7 +391,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(&out_map)),
                          "r"(my_buf), "r"(ob * 128 + h * 64 + cb * 32), "r"((int32_t)(m0 + q * 32))
@@ -494,7 +401,7 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
         }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
 
   tc_fence_before();
@@ -505,10 +412,11 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool g_attr_set = false;
 
+}  // namespace
+
+namespace tc {
 EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -522,36 +430,45 @@ EncodeTiledFn get_encode() {
   }
   return fn;
 }
-
-int g_num_sms = 0;
-bool g_attr_set = false;
-
-}  // namespace
+int make_map_2d(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn encode = get_encode();
+  LGCN_CHECK_ARG(encode != nullptr, "linear128(tcgen05): cuTensorMapEncodeTiled not available from the driver");
+  LGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "linear128(tcgen05): tensor must be 16-byte aligned");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LGCN_CHECK_ARG(r == CUDA_SUCCESS, "linear128(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+int make_out_map(CUtensorMap* map, float* out, int64_t cols, int64_t rows, int64_t ldo) {
+  return make_map_2d(map, out, cols, rows, ldo, 32, 32);
+}
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+}  // namespace tc
 
 int lgcn_launch_linear_tc(const LinearArgs& a, cudaStream_t st) {
   if (a.m <= 0) return 0;
-  EncodeTiledFn encode = get_encode();
-  LGCN_CHECK_ARG(encode != nullptr, "linear128(tcgen05): cuTensorMapEncodeTiled not available from the driver");
   LGCN_CHECK_ARG(a.n_src == 1 || a.n_out_blocks == 1, "linear128(tcgen05): several sources need n_out_blocks == 1");
-  LGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "linear128(tcgen05): out must be 16-byte aligned");
+  // (the LaneConv stack routes its 15-block projection to gemm_tc_wide.cu, which needs pre-split weights)
   if (!g_attr_set) {
-    int dev = 0;
-    LGCN_CUDA_OK(cudaGetDevice(&dev));
-    LGCN_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     g_attr_set = true;
   }
   CUtensorMap map;
-  const cuuint64_t dims[2] = {(cuuint64_t)a.n_out_blocks * LGCN_C, (cuuint64_t)a.m};
-  const cuuint64_t strides[1] = {(cuuint64_t)a.ldo * sizeof(float)};
-  const cuuint32_t box[2] = {32, 32};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.out, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LGCN_CHECK_ARG(r == CUDA_SUCCESS, "linear128(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  if (int rc = make_out_map(&map, a.out, (int64_t)a.n_out_blocks * LGCN_C, a.m, a.ldo)) return rc;
   const int64_t n_tiles = (a.m + kTileM - 1) / kTileM;
-  const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
+  const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
   k_linear_tc<<<grid, kNumThreads, kSmemTotal, st>>>(a, map);
   LGCN_LAUNCH_OK();
   return 0;
