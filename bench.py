@@ -211,27 +211,43 @@ def run_ours(args):
     ms_per_step = float(t.item()) / args.steps
     value = B / (ms_per_step / 1e3)
 
-    # ---- end to end: collated CPU dict -> outputs on the host, wall clock, max over ranks
-    def step_e2e():
-        out = net(data)
+    # ---- end to end: collated CPU dicts -> cls/reg on the host.  Every step packs its batch into pinned memory,
+    # copies it H2D, runs the forward and reads the result back (D2H); the staging of step i+1 is overlapped with
+    # the device work of step i (lanegcn.prefetch_forward — a DataLoader-style prefetch).  Wall clock, max over
+    # ranks.  The un-overlapped latency of one Net.forward(data) + D2H call is reported next to it.
+    def finish(out):
         if world > 1:
-            out = shard.gather_outputs(out, shard.make_plan([len(c) for c in data["ctrs"]]))
+            out = shard.gather_outputs(out, plan)
         return torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
 
-    for _ in range(3):
-        cls, reg = step_e2e()
+    def run_e2e(n):
+        for out in L.prefetch_forward(net, (data for _ in range(n))):
+            res = finish(out)
+        return res
+
+    run_e2e(3)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cls, reg = step_e2e()
+    for _ in range(5):
+        net.stage(data)
+    stage_host_ms = 1e3 * (time.perf_counter() - t0) / 5
+    sync_all()
+    t0 = time.perf_counter()
+    cls, reg = run_e2e(args.steps)
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        finish(net(data))
+    torch.cuda.synchronize()
+    lat_ms = 1e3 * (time.perf_counter() - t0) / 3
+    te = torch.tensor([e2e_ms, lat_ms], dtype=torch.float64, device=dev)
     hb = torch.tensor([float(net.stage(data).h2d_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(hb, op=dist.ReduceOp.SUM)
-    e2e_ms = float(te.item())
+    e2e_ms, lat_ms = float(te[0].item()), float(te[1].item())
     d2h = int(cls.numel() * 4 + reg.numel() * 4) * (world if world > 1 else 1)  # every rank reads the gathered result
 
     if rank != 0:
@@ -271,6 +287,9 @@ def run_ours(args):
                          f"{n_nodes * 1920 * 4 / 1e6:.0f} MB) exceeds the 126 MB L2",
                    "kernel_ms_per_step": step_kernel_ms},
         "e2e": {"value": round(B / (e2e_ms / 1e3), 2), "unit": "scenes/s", "ms_per_step": round(e2e_ms, 4),
+                "single_call_latency_ms": round(lat_ms, 4), "stage_host_ms": round(stage_host_ms, 4),
+                "how": "Net.stage (pack into pinned memory + H2D) + Net.forward_device + D2H of cls/reg every step; "
+                       "staging of step i+1 overlapped with the device work of step i (prefetch_forward)",
                 "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(lt.item()),
         "roofline": {"kernel": "k_gather_gn_relu (LaneConv gather + GN + ReLU)", "bound": "hbm",

@@ -53,6 +53,13 @@ int64_t lgcn_launch_count(void);
 int lgcn_prof_enable(int on);
 int lgcn_prof_collect(double* h_ms_by_kind, int64_t* h_launches_by_kind);
 
+/* ------------------------------------------------------------------ host staging
+ * Copies n host arrays (h_srcs[i], h_nbytes[i] bytes) back to back into the host arena h_dst (normally pinned
+ * memory, dst_bytes capacity) with n_threads copy threads.  Host-only; replaces the per-tensor cudaMemcpyAsync of
+ * utils.gpu (utils.py:74-85) together with ONE cudaMemcpyAsync of the arena by the caller.                      */
+int lgcn_pack_host(const void* const* h_srcs, const int64_t* h_nbytes, int64_t n, void* h_dst, int64_t dst_bytes,
+                   int n_threads);
+
 /* ------------------------------------------------------------------ graph batching
  * replaces utils.to_long (utils.py:88-96) + the offset/cat loops of graph_gather (lanegcn.py:191-208).
  * `local` holds S segments of scene-local indices (idx_bytes = 2, 4 or 8: int16/int32/int64) laid out
@@ -76,6 +83,23 @@ int64_t lgcn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges);
 int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len, int n_keys,
                    int64_t n_nodes, int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag,
                    void* stream);
+
+/* ------------------------------------------------------------------ multi-scale dilation (data.py:520-534)
+ * Boolean CSR squaring with scipy's column order (reverse first discovery), bit-exact.  int32 CSR on the device.
+ *   lgcn_dilate_csr0   : scale-0 edge list (int64 u = row, v = col; duplicates merged, columns ascending) -> CSR;
+ *                        rowptr int32[n+1], col int32[>= n_edges]; *h_nnz = number of stored entries.
+ *   lgcn_dilate_bound  : upper bound of nnz(A*A) (also prepares the per-row scratch offsets inside `workspace`).
+ *   lgcn_dilate_square : A*A -> rowptr_out/col_out (+ optional COO int64 u_out/v_out, i.e. the `u`,`v` the reference
+ *                        returns for that scale); needs cap >= the bound, on the SAME workspace as the bound call.
+ * All three SYNCHRONISE the stream to return their host counts (dataset-build-time code, not the forward path).
+ * workspace: lgcn_dilate_workspace_bytes(n_nodes, cap) with cap >= max(n_edges, bound).                          */
+int64_t lgcn_dilate_workspace_bytes(int64_t n_nodes, int64_t cap);
+int lgcn_dilate_csr0(const int64_t* u, const int64_t* v, int64_t n_edges, int64_t n_nodes, int32_t* rowptr,
+                     int32_t* col, void* workspace, int64_t* h_nnz, void* stream);
+int lgcn_dilate_bound(const int32_t* rowptr, const int32_t* col, int64_t n_nodes, void* workspace, int64_t* h_bound,
+                      void* stream);
+int lgcn_dilate_square(const int32_t* rowptr, const int32_t* col, int64_t n_nodes, int64_t cap, int32_t* rowptr_out,
+                       int32_t* col_out, int64_t* u_out, int64_t* v_out, void* workspace, int64_t* h_nnz, void* stream);
 
 /* ------------------------------------------------------------------ dense pieces
  * out[m, ob*128 + c] (row stride ldo) for ob in [0, n_out_blocks):

@@ -28,10 +28,15 @@ _SIGS = {
     "lgcn_launch_count": (_i64, []),
     "lgcn_prof_enable": (_i32, [_i32]),
     "lgcn_prof_collect": (_i32, [_vp, _vp]),
+    "lgcn_pack_host": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32]),
     "lgcn_offset_indices": (_i32, [_vp, _i32, _vp, _vp, _i32, _i64, _vp, _vp]),
     "lgcn_pack_meta": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_csr_build": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lgcn_dilate_workspace_bytes": (_i64, [_i64, _i64]),
+    "lgcn_dilate_csr0": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lgcn_dilate_bound": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "lgcn_dilate_square": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_linear128": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32,
                               _vp, _i64, _i64, _vp]),
     "lgcn_mlp2_in": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

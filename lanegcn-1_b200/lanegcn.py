@@ -16,6 +16,7 @@ import ctypes
 import os
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 from torch import Tensor, nn
 
@@ -53,7 +54,10 @@ def scene_list(cat: Tensor, sizes: List[int], off_dev: Optional[Tensor] = None) 
     for s in sizes:
         off.append(off[-1] + s)
     out.off = off
-    out.off_dev = off_dev if off_dev is not None else torch.tensor(off, dtype=torch.int32, device=cat.device)
+    if off_dev is None:  # through pinned memory: a pageable H2D copy would block the host behind queued device work
+        off_t = torch.tensor(off, dtype=torch.int32)
+        off_dev = _stage(off_t, cat.device, torch.int32, "scene_off") if cat.is_cuda else off_t
+    out.off_dev = off_dev
     return out
 
 
@@ -193,6 +197,51 @@ def _packed_of(graph: dict) -> PackedGraph:
     return pg
 
 
+# --------------------------------------------------------------------------- dilated_nbrs (data.py:520-534)
+def dilated_nbrs(nbr: Dict, num_nodes: int, num_scales: int, device=None) -> List[Dict[str, Tensor]]:
+    """Scales 1..num_scales-1 (hops 2,4,8,...) of a scale-0 edge set ``{"u","v"}`` by repeated boolean squaring
+    on the GPU — same signature and results as the reference's scipy version (data.py:520-534): ``u`` ascending,
+    ``v`` in scipy's per-row order, int64, bit-exact.  ``num_nodes`` may be the node count of a whole BATCHED graph
+    (the adjacency is block diagonal, so all scenes are dilated at once).  Returns CUDA tensors."""
+    lib = _C.lib()
+    u, v = torch.as_tensor(nbr["u"]), torch.as_tensor(nbr["v"])
+    dev = device or (u.device if u.is_cuda else _target_device(u))
+    u, v = u.to(dev, torch.int64).contiguous(), v.to(dev, torch.int64).contiguous()
+    n, e0 = int(num_nodes), int(u.numel())
+    st = _C.stream_ptr()
+    cnt = ctypes.c_int64(0)
+
+    def workspace(cap):
+        return torch.empty(lib.lgcn_dilate_workspace_bytes(n, cap), dtype=torch.uint8, device=dev)
+
+    ws = workspace(e0)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(e0, 1), dtype=torch.int32, device=dev)
+    _C.check(lib.lgcn_dilate_csr0(u.data_ptr(), v.data_ptr(), e0, n, rowptr.data_ptr(), col.data_ptr(), ws.data_ptr(),
+                                  ctypes.byref(cnt), st), "dilate_csr0")
+    cap, out = max(2 * cnt.value, 1024), []
+    ws = workspace(cap)
+    for _ in range(1, num_scales):
+        _C.check(lib.lgcn_dilate_bound(rowptr.data_ptr(), col.data_ptr(), n, ws.data_ptr(), ctypes.byref(cnt), st),
+                 "dilate_bound")
+        if cnt.value > cap:
+            cap = cnt.value
+            ws = workspace(cap)
+            _C.check(lib.lgcn_dilate_bound(rowptr.data_ptr(), col.data_ptr(), n, ws.data_ptr(), ctypes.byref(cnt), st),
+                     "dilate_bound")
+        m = max(cnt.value, 1)
+        rowptr2 = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col2 = torch.empty(m, dtype=torch.int32, device=dev)
+        uo, vo = torch.empty(m, dtype=torch.int64, device=dev), torch.empty(m, dtype=torch.int64, device=dev)
+        _C.check(lib.lgcn_dilate_square(rowptr.data_ptr(), col.data_ptr(), n, cap, rowptr2.data_ptr(), col2.data_ptr(),
+                                        uo.data_ptr(), vo.data_ptr(), ws.data_ptr(), ctypes.byref(cnt), st),
+                 "dilate_square")
+        nnz = cnt.value
+        out.append({"u": uo[:nnz], "v": vo[:nnz]})
+        rowptr, col = rowptr2, col2
+    return out
+
+
 # --------------------------------------------------------------------------- actor_gather / graph_gather
 def actor_gather(actors: List[Tensor]):
     """lanegcn.py:155-168 — list of [A_i,20,3] -> ([sum A,3,20], per-scene index lists)."""
@@ -315,6 +364,9 @@ def _target_device(t: Tensor):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_PACK_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
+
+
 class _PinnedPool:
     """Reusable page-locked staging buffers (cudaHostAlloc costs milliseconds, so never per batch).  A slot is
     reused only after the async H2D copy that last read it has completed (event per slot)."""
@@ -339,12 +391,18 @@ def _stage_cat(parts: List[Tensor], dev, dtype, tag: str) -> Tensor:
     Device inputs are concatenated on the device."""
     if parts[0].is_cuda:
         return torch.cat([p.to(dtype) for p in parts])
-    n = sum(p.numel() for p in parts)
-    esz = torch.empty(0, dtype=dtype).element_size()
-    ring, i, buf = _PinnedPool.take(tag, n * esz)
-    host = buf[: n * esz].view(dtype)
+    if {p.dtype for p in parts} != {dtype} or not all(p.is_contiguous() for p in parts):
+        parts = [p.to(dtype).contiguous() for p in parts]
+    k = len(parts)
+    sizes = np.fromiter((p.nbytes for p in parts), np.int64, k)
+    ptrs = np.fromiter((p.data_ptr() for p in parts), np.uint64, k)
+    nbytes = int(sizes.sum())
+    n = nbytes // parts[0].element_size()
+    ring, i, buf = _PinnedPool.take(tag, nbytes)
+    host = buf[:nbytes].view(dtype)
     if n:
-        torch.cat(parts, out=host) if all(p.dtype == dtype for p in parts) else torch.cat([p.to(dtype) for p in parts], out=host)
+        _C.check(_C.lib().lgcn_pack_host(ptrs.ctypes.data, sizes.ctypes.data, k, buf.data_ptr(), nbytes, _PACK_THREADS),
+                 "pack_host")
     out = host.to(dev, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
@@ -743,13 +801,20 @@ class Net(nn.Module):
             sizes = [len(x) for x in data["feats"]]
             b.actors = _stage(torch.cat(list(data["feats"]), 0), dev, torch.float32, "actors")
             b.actor_ctrs = scene_list(_stage(torch.cat(list(data["ctrs"]), 0), dev, torch.float32, "actr"), sizes)
-            b.rot = _stage(torch.stack(list(data["rot"])), dev, torch.float32, "rot")
-            b.orig = _stage(torch.stack(list(data["orig"])), dev, torch.float32, "orig")
-            b.rot_a = torch.repeat_interleave(b.rot, torch.tensor(sizes, device=dev), 0, output_size=sum(sizes))
-            b.orig_a = torch.repeat_interleave(b.orig, torch.tensor(sizes, device=dev), 0, output_size=sum(sizes))
+            rot, orig = torch.stack(list(data["rot"])), torch.stack(list(data["orig"]))
+            b.rot = _stage(rot, dev, torch.float32, "rot")
+            b.orig = _stage(orig, dev, torch.float32, "orig")
+            if rot.is_cuda:
+                cnt = torch.tensor(sizes, device=dev)
+                b.rot_a, b.orig_a = torch.repeat_interleave(b.rot, cnt, 0), torch.repeat_interleave(b.orig, cnt, 0)
+            else:  # expand per actor on the host and stage through pinned memory: a pageable H2D copy here would
+                #    block the host behind all queued device work and serialise prefetch_forward
+                cnt = torch.tensor(sizes)
+                b.rot_a = _stage(torch.repeat_interleave(rot.float(), cnt, 0), dev, torch.float32, "rot_a")
+                b.orig_a = _stage(torch.repeat_interleave(orig.float(), cnt, 0), dev, torch.float32, "orig_a")
             b.graphs = stage_graphs(data["graph"])
             b.h2d_bytes = b.graphs.h2d_bytes + 4 * (b.actors.numel() + b.actor_ctrs.cat.numel() + b.rot.numel()
-                                                    + b.orig.numel()) + 12 * (len(sizes) + 1)
+                                                    + b.orig.numel() + b.rot_a.numel() + b.orig_a.numel()) + 12 * (len(sizes) + 1)
             return b
 
     @torch.no_grad()
@@ -792,6 +857,26 @@ class Net(nn.Module):
             else:
                 cls, reg = self._pred_core(actors, actor_ctrs.cat, b.rot_a, b.orig_a)
             return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
+
+
+def prefetch_forward(net: "Net", batches):
+    """Generator over collated CPU batches -> outputs, with the host staging of batch i+1 (pack + H2D) overlapped
+    with the device work of batch i: what a DataLoader with pinned prefetch gives the reference's training loop
+    (train.py:118-143, ``pin_memory=True``).  Every batch still goes through ``Net.stage`` + ``Net.forward_device``,
+    i.e. exactly ``Net.forward`` split at the H2D boundary."""
+    it = iter(batches)
+    try:
+        staged = net.stage(next(it))
+    except StopIteration:
+        return
+    while staged is not None:
+        out = net.forward_device(staged)          # enqueued; the host returns after the one pair-count sync
+        try:
+            nxt = net.stage(next(it))             # host packing + H2D of the next batch while the GPU computes
+        except StopIteration:
+            nxt = None
+        yield out
+        staged = nxt
 
 
 def get_model():

@@ -104,6 +104,42 @@ def test_csr_handles_empty_sets_hubs_and_bad_indices(cuda, lib):
         pg.check()
 
 
+# --------------------------------------------------------------------------- dilation (a13)
+def test_dilated_nbrs_bit_exact_vs_reference_golden(cuda, lib):
+    g = golden("dilate_tiny")
+    graph = golden_scenes("tiny_b3")[0]["graph"]
+    for d in ("pre", "suc"):
+        got = L.dilated_nbrs({"u": graph[d][0]["u"], "v": graph[d][0]["v"]}, graph["num_nodes"], 6)
+        assert len(got) == 5
+        for i, e in enumerate(got):
+            assert e["u"].dtype == torch.int64 and e["u"].is_cuda
+            assert np.array_equal(e["u"].cpu().numpy(), g[f"{d}{i + 1}_u"]), (d, i)
+            assert np.array_equal(e["v"].cpu().numpy(), g[f"{d}{i + 1}_v"]), (d, i)
+
+
+def test_dilated_nbrs_batched_branching_and_duplicates(cuda, lib):
+    """Random branching graph with duplicate edges and empty rows vs scipy (the reference's data path) and vs the
+    numpy restatement; then a whole batch dilated at once == the scenes dilated one by one."""
+    rng = np.random.default_rng(3)
+    n = 400
+    u = np.concatenate([np.arange(1, n), rng.integers(0, n, 150), rng.integers(0, n, 40)])
+    v = np.concatenate([np.arange(0, n - 1), rng.integers(0, n, 150), rng.integers(0, n, 40)])
+    u, v = np.concatenate([u, u[:30]]), np.concatenate([v, v[:30]])  # duplicates
+    want = synth.dilate_edges(u, v, n, 5)
+    mine = graph_oracle.dilate_smmp(u, v, n, 5)
+    got = L.dilated_nbrs({"u": u, "v": v}, n, 5)
+    for w, m, gt in zip(want, mine, got):
+        assert np.array_equal(m["u"], w["u"]) and np.array_equal(m["v"], w["v"])
+        assert np.array_equal(gt["u"].cpu().numpy(), w["u"]) and np.array_equal(gt["v"].cpu().numpy(), w["v"])
+    scenes = golden_scenes("tiny_b3")
+    batch = synth.collate(scenes)
+    bg = O.graph_gather(O.to_long(batch["graph"]))
+    n_tot = bg["feats"].shape[0]
+    got = L.dilated_nbrs({"u": bg["pre"][0]["u"], "v": bg["pre"][0]["v"]}, n_tot, 6)
+    for s in range(1, 6):
+        assert torch.equal(got[s - 1]["u"].cpu(), bg["pre"][s]["u"]) and torch.equal(got[s - 1]["v"].cpu(), bg["pre"][s]["v"])
+
+
 # --------------------------------------------------------------------------- pair lists (a10)
 @pytest.mark.parametrize("name", ["tiny_b3", "argo_b1"])
 def test_pair_lists_bit_exact(cuda, lib, name):
