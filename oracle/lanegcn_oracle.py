@@ -277,3 +277,19 @@ def net_forward(sd: Dict[str, Tensor], data: dict, taps: dict | None = None) -> 
     for i in range(len(out["reg"])):
         out["reg"][i] = torch.matmul(out["reg"][i], data["rot"][i]) + data["orig"][i].view(1, 1, 1, -1)
     return out
+
+
+# --------------------------------------------------------------------------- LaneRCNN lane-graph layers
+def lane_roi(sd, prefix: str, feat: Tensor, graph: dict) -> Tensor:
+    """lanercnn.py:388-430 — input Linear+GN+ReLU, then the LaneConv loop (empty edge sets are skipped there by
+    `len > 0` guards; index_add_ with empty indices is a no-op, so the shared loop restates it)."""
+    feat = linear_gn(feat, sd, prefix + ".input", act=True)
+    g = dict(graph)
+    for d in ("pre", "suc"):
+        g[d] = list(graph[d])
+    return lane_conv_stack(sd, prefix, feat, g)
+
+
+def global_graph_net(sd, prefix: str, feat: Tensor, graph: dict) -> Tensor:
+    """lanercnn.py:552-600 — identical to the M2M loop."""
+    return lane_conv_stack(sd, prefix, feat, graph)
