@@ -87,8 +87,8 @@ class _Workspace:
 _SIDE_STREAMS: Dict = {}
 
 
-def _side_stream(device):
-    key = str(device)
+def _side_stream(device, tag: str = "side"):
+    key = (str(device), tag)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -453,17 +453,36 @@ class PairList:
         return self
 
 
-def build_pair_lists(specs, want_int64: bool = False) -> List[PairList]:
-    """Pair lists for several (agt_ctrs, ctx_ctrs, th) triples with ONE host synchronisation in total
-    (the reference synchronises once per scene per Att layer: lanegcn.py:680-681)."""
+def count_pair_lists(specs) -> List[PairList]:
+    """Enqueue the count kernels of several (agt_ctrs, ctx_ctrs, th) triples; no host synchronisation."""
     pls = [PairList(_as_scene_list(a), _as_scene_list(c), th) for a, c, th in specs]
     for p in pls:
         _need_cuda(p.agt.cat, "agent centres")
         p.count()
-    totals = torch.stack([p.rowptr[-1] for p in pls]).tolist()  # the one D2H sync
+    return pls
+
+
+def fill_pair_lists(pls: List[PairList], want_int64: bool = False, counted: "torch.cuda.Event" = None) -> List[PairList]:
+    """Read the pair totals (ONE device->host synchronisation for all lists) and enqueue the fill kernels.
+    With ``counted`` (an event recorded right after the count kernels) the read-back runs on an auxiliary stream
+    that waits for that event only, so work enqueued on the main stream in the meantime keeps the device busy
+    and the host does not wait for it."""
+    if counted is None:
+        totals = torch.stack([p.rowptr[-1] for p in pls]).tolist()  # the one D2H sync
+    else:
+        aux = _side_stream(pls[0].rowptr.device, "aux")
+        aux.wait_event(counted)
+        with torch.cuda.stream(aux):
+            totals = torch.stack([p.rowptr[-1] for p in pls]).tolist()
     for p, n in zip(pls, totals):
         p.fill(n, want_int64)
     return pls
+
+
+def build_pair_lists(specs, want_int64: bool = False) -> List[PairList]:
+    """Pair lists for several (agt_ctrs, ctx_ctrs, th) triples with ONE host synchronisation in total
+    (the reference synchronises once per scene per Att layer: lanegcn.py:680-681)."""
+    return fill_pair_lists(count_pair_lists(specs), want_int64)
 
 
 def att_pairs(agt_ctrs, ctx_ctrs, dist_th: float):
@@ -830,20 +849,25 @@ class Net(nn.Module):
             actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev)
             graph = finish_graph(b.graphs)                                        # lanegcn.py:134
             node_ctrs = graph["ctrs"]
-            # the three pair lists depend on centres only: build them up front with ONE host sync
-            p_a2m, p_m2a, p_a2a = build_pair_lists([
+            # the three pair lists depend on centres only: count them up front ...
+            pls = count_pair_lists([
                 (node_ctrs, actor_ctrs, cfg["actor2map_dist"]),
                 (actor_ctrs, node_ctrs, cfg["map2actor_dist"]),
                 (actor_ctrs, actor_ctrs, cfg["actor2actor_dist"]),
             ])
-            # MapNet is a handful of C-ABI calls: enqueue it FIRST so the GPU is busy while the host launches
-            # ActorNet (stock PyTorch; independent of the map) on a side stream; join before A2M.
+            # ... enqueue MapNet (a handful of C-ABI calls, milliseconds of device work) and ActorNet (stock PyTorch,
+            # independent of the map, on a side stream) ...
             cur, side = torch.cuda.current_stream(), _side_stream(b.actors.device)
             side.wait_stream(cur)
+            counted = torch.cuda.Event()
+            counted.record(cur)
             nodes, node_idcs, node_ctrs = self.map_net(graph)                     # :135
             with torch.cuda.stream(side):
                 x = b.actors.transpose(1, 2).contiguous()
                 actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
+            # ... and only now take the ONE host synchronisation of the forward (three pair totals), on an auxiliary
+            # stream that waits for the count kernels only: the device stays busy with MapNet meanwhile.
+            p_a2m, p_m2a, p_a2a = fill_pair_lists(pls, counted=counted)
             cur.wait_stream(side)
             actors.record_stream(cur)
             nodes = self.a2m(nodes, graph, actors, actor_idcs, actor_ctrs, pairs=p_a2m)   # :138
