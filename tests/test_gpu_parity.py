@@ -416,3 +416,59 @@ def test_batch128_properties(cuda, lib, net):
     for k in ("cls", "reg"):
         got = halves[0][k] + halves[1][k]
         assert_close(torch.cat(got), torch.cat(out1[k]), "sharded " + k, rtol=1e-5, atol=1e-5)
+
+
+# --------------------------------------------------------------------------- config 4: one city-scale lane graph
+def test_mapnet_city_100k_vs_oracle(cuda, lib, net):
+    """BASELINE configs[3]: MapNet alone on a single ~100k-node graph (int64 indices: the scene exceeds the int16
+    range of the preprocessed pickles), against the CPU oracle."""
+    scene = synth.make_scene(0, "city-100k")
+    assert scene["graph"]["num_nodes"] == 100800 and scene["graph"]["pre"][0]["u"].dtype == np.int64
+    batch = synth.collate([scene])
+    sd = weights()
+    og = O.graph_gather(O.to_long(batch["graph"]))
+    with torch.no_grad():
+        want, _, _ = O.map_net(sd, og)
+    graph = L.graph_gather(batch["graph"])
+    graph["_packed"].check()
+    assert torch.equal(graph["suc"][4]["v"].cpu(), og["suc"][4]["v"])
+    got, _, _ = net.map_net(graph)
+    assert_close(got, want, "map_net (100,800 nodes)")
+
+
+# --------------------------------------------------------------------------- property tests (random inputs)
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=20, deadline=None)
+@given(st.integers(1, 300), st.integers(0, 6), st.integers(0, 2**31 - 1))
+def test_csr_random_edge_sets(n, n_keys, seed):
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(seed)
+    sets = []
+    for _ in range(n_keys):
+        e = int(rng.integers(0, 4 * n))
+        sets.append((rng.integers(0, n, e), rng.integers(0, n, e)))
+    rowptr, col = graph_oracle.merged_csr(sets, n, n_keys)
+    es = [{"u": torch.from_numpy(u).to(dev), "v": torch.from_numpy(v).to(dev)} for u, v in sets]
+    pg = L.build_csr(es, n, dev)
+    pg.check()
+    assert np.array_equal(pg.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(pg.col.cpu().numpy()[: len(col)], col)
+
+
+@settings(max_examples=20, deadline=None)
+@given(st.integers(1, 5), st.floats(0.5, 30.0), st.integers(0, 2**31 - 1))
+def test_pairs_random_scenes(n_scenes, th, seed):
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(seed)
+    agt = [rng.uniform(-20, 20, (int(rng.integers(1, 60)), 2)).astype(np.float32) for _ in range(n_scenes)]
+    ctx = [rng.uniform(-20, 20, (int(rng.integers(1, 90)), 2)).astype(np.float32) for _ in range(n_scenes)]
+    if n_scenes > 2:
+        ctx[1] = ctx[1] + np.float32(500.0)  # an empty scene in the middle
+    th = float(np.float32(th))
+    want_hi, want_wi = graph_oracle.pair_list(agt, ctx, th)
+    if len(want_hi) == 0:
+        return
+    hi, wi = L.att_pairs([torch.from_numpy(x).to(dev) for x in agt], [torch.from_numpy(x).to(dev) for x in ctx], th)
+    assert np.array_equal(hi.cpu().numpy(), want_hi) and np.array_equal(wi.cpu().numpy(), want_wi)
