@@ -84,6 +84,13 @@ int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const i
                    int64_t n_nodes, int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag,
                    void* stream);
 
+/* Stable destination-sorted CSR of ONE scatter  out[dst[e]] += rows[src[e]]  (what CPU index_add_ does on an unsorted
+ * destination index, in edge order): rowptr int32[n_dst+1], col int32[n_edges] = src in CSR order.  dst in [0,n_dst),
+ * src in [0,n_src); violations set *err_flag.  Workspace: lgcn_csr_workspace_bytes(n_dst, n_edges).  Used by the
+ * LaneRCNN clients (LanePooling scatters on wi, lanercnn.py:506; LaneInput on a2m.v, :327-331).               */
+int lgcn_scatter_csr_build(const int64_t* dst, const int64_t* src, int64_t n_edges, int64_t n_dst, int64_t n_src,
+                           int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag, void* stream);
+
 /* ------------------------------------------------------------------ multi-scale dilation (data.py:520-534)
  * Boolean CSR squaring with scipy's column order (reverse first discovery), bit-exact.  int32 CSR on the device.
  *   lgcn_dilate_csr0   : scale-0 edge list (int64 u = row, v = col; duplicates merged, columns ascending) -> CSR;
@@ -122,12 +129,24 @@ int lgcn_linear128(const float* a0, const int32_t* idx0, const float* a1, const 
 int lgcn_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
                  const float* b1, float* h, int64_t m, void* stream);
 
+/* Same for 4-float rows: h[m,:] = relu(W1[128,4] . (p[ip[m]] - q[iq[m]]) + b1) — LanePooling.relpose on pose
+ * differences (lanercnn.py:443-446, 494-495).                                                              */
+int lgcn_mlp4_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
+                 const float* b1, float* h, int64_t m, void* stream);
+
 /* LaneConv gather-reduce with fused GroupNorm(1)+ReLU (lanegcn.py:333-357 after the wide projection):
  *   t = Y[n, 0:128];  for e in rowptr[n]..rowptr[n+1]: t += Y_blocks[col[e]];  out[n] = relu(GN(t))
  * Y is [n_nodes, n_blocks*128]; Y_blocks[b] = Y + b*128 floats.  Fixed summation order => deterministic. */
 int lgcn_laneconv_gather_gn_relu(const float* Y, int n_blocks, const int32_t* rowptr, const int32_t* col,
                                  const float* gamma, const float* beta, float* out, int64_t n_nodes,
                                  void* stream);
+
+/* General form: out[r] = relu(GN(base[r*base_ld ..+128] + sum_e blocks[col[e]*128 ..+128])) over rowptr[r]..rowptr[r+1],
+ * in CSR order.  Replaces index_add_ on an UNSORTED destination index (LanePooling scatters on wi, lanercnn.py:506;
+ * LaneInput on a2m.v, :327-331) once the caller has a stable destination-sorted CSR (lgcn_csr_build).        */
+int lgcn_gather_rows_gn_relu(const float* base, int64_t base_ld, const float* blocks, const int32_t* rowptr,
+                             const int32_t* col, const float* gamma, const float* beta, float* out, int64_t n_rows,
+                             void* stream);
 
 /* Att scatter (lanegcn.py:702-705): out[r] = relu(GN(a[r] + sum_{p in rowptr[r]..rowptr[r+1]} c[p])).
  * Pairs are destination-sorted already (hi ascending), so the segments are contiguous rows of c.         */

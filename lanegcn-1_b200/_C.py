@@ -33,6 +33,7 @@ _SIGS = {
     "lgcn_pack_meta": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_csr_build": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lgcn_scatter_csr_build": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_dilate_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_dilate_csr0": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_dilate_bound": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
@@ -40,6 +41,8 @@ _SIGS = {
     "lgcn_linear128": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32,
                               _vp, _i64, _i64, _vp]),
     "lgcn_mlp2_in": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "lgcn_mlp4_in": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "lgcn_gather_rows_gn_relu": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_laneconv_gather_gn_relu": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_segsum_gn_relu": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_pairs_workspace_bytes": (_i64, [_i64, _i32]),

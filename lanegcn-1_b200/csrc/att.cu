@@ -230,6 +230,39 @@ k_mlp2_in(const float2* __restrict__ p, const int32_t* __restrict__ ip, const fl
   }
 }
 
+// nn.Linear(4,128) + bias + ReLU on x = p[ip[m]] - q[iq[m]] (4 floats per row): LanePooling.relpose, lanercnn.py:443-446
+__global__ void __launch_bounds__(256)
+k_mlp4_in(const float4* __restrict__ p, const int32_t* __restrict__ ip, const float4* __restrict__ q,
+          const int32_t* __restrict__ iq, const float* __restrict__ W1, const float* __restrict__ b1,
+          float* __restrict__ h, int64_t m) {
+  const int lane = threadIdx.x & 31;
+  float4 w[4];  // rows lane*4 .. lane*4+3 of W1 [128,4]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) w[j] = reinterpret_cast<const float4*>(W1)[lane * 4 + j];
+  const float4 bb = reinterpret_cast<const float4*>(b1)[lane];
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < m; r += (int64_t)gridDim.x * 8) {
+    float4 x = p[ip ? ip[r] : r];
+    if (q) {
+      const float4 y = q[iq ? iq[r] : r];
+      x.x -= y.x; x.y -= y.y; x.z -= y.z; x.w -= y.w;
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaf(x.w, w[j].w, fmaf(x.z, w[j].z, fmaf(x.y, w[j].y, x.x * w[j].x)));
+    reinterpret_cast<float4*>(h + r * LGCN_C)[lane] =
+        make_float4(fmaxf(o[0] + bb.x, 0.f), fmaxf(o[1] + bb.y, 0.f), fmaxf(o[2] + bb.z, 0.f), fmaxf(o[3] + bb.w, 0.f));
+  }
+}
+
+extern "C" int lgcn_mlp4_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
+                            const float* b1, float* h, int64_t m, void* stream) {
+  if (m <= 0) return 0;
+  const unsigned grid = min(lgcn_cdiv(m, 8), 148u * 32u);
+  k_mlp4_in<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)p, ip, (const float4*)q, iq, W1, b1, h, m);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int lgcn_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq,
                             const float* W1, const float* b1, float* h, int64_t m, void* stream) {
   if (m <= 0) return 0;

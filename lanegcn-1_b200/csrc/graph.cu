@@ -159,12 +159,12 @@ __device__ __forceinline__ int key_of(const EdgeSets& es, int64_t e) {
   return k;
 }
 
-__global__ void k_csr_hist(EdgeSets es, int64_t n_nodes, int32_t* __restrict__ cnt, int32_t* __restrict__ err) {
+__global__ void k_csr_hist(EdgeSets es, int64_t n_nodes, int64_t n_src, int32_t* __restrict__ cnt, int32_t* __restrict__ err) {
   const int64_t E = es.start[es.n_keys];
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     const int k = key_of(es, e);
     const int64_t u = es.u[k][e - es.start[k]], v = es.v[k][e - es.start[k]];
-    if (u < 0 || u >= n_nodes || v < 0 || v >= n_nodes) {
+    if (u < 0 || u >= n_nodes || v < 0 || v >= n_src) {
       atomicExch(err, 1);
       continue;
     }
@@ -172,13 +172,13 @@ __global__ void k_csr_hist(EdgeSets es, int64_t n_nodes, int32_t* __restrict__ c
   }
 }
 
-__global__ void k_csr_place(EdgeSets es, int64_t n_nodes, const int32_t* __restrict__ rowptr,
+__global__ void k_csr_place(EdgeSets es, int64_t n_nodes, int64_t n_src, const int32_t* __restrict__ rowptr,
                             int32_t* __restrict__ cursor, int32_t* __restrict__ slot_edge) {
   const int64_t E = es.start[es.n_keys];
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     const int k = key_of(es, e);
     const int64_t u = es.u[k][e - es.start[k]], v = es.v[k][e - es.start[k]];
-    if (u < 0 || u >= n_nodes || v < 0 || v >= n_nodes) continue;
+    if (u < 0 || u >= n_nodes || v < 0 || v >= n_src) continue;
     const int32_t pos = atomicAdd(&cursor[u], 1);
     slot_edge[rowptr[u] + pos] = (int32_t)e;
   }
@@ -188,7 +188,7 @@ __global__ void k_csr_place(EdgeSets es, int64_t n_nodes, const int32_t* __restr
 // the stable-by-destination order CPU index_add_ accumulates in) and emit col = v*(K+1) + (k+1).
 // Rows are short (about a dozen entries on lane graphs), so an in-place insertion sort is the right tool;
 // the atomics above only decide a scratch order that this pass erases, so the CSR is deterministic.
-__global__ void k_csr_finish(EdgeSets es, int64_t n_nodes, const int32_t* __restrict__ rowptr,
+__global__ void k_csr_finish(EdgeSets es, int64_t n_nodes, int plain, const int32_t* __restrict__ rowptr,
                              int32_t* __restrict__ slot_edge, int32_t* __restrict__ col) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_nodes) return;
@@ -206,7 +206,8 @@ __global__ void k_csr_finish(EdgeSets es, int64_t n_nodes, const int32_t* __rest
   for (int32_t i = beg; i < end; ++i) {
     const int64_t e = slot_edge[i];
     const int k = key_of(es, e);
-    col[i] = (int32_t)(es.v[k][e - es.start[k]] * nb + (k + 1));
+    const int64_t v = es.v[k][e - es.start[k]];
+    col[i] = plain ? (int32_t)v : (int32_t)(v * nb + (k + 1));
   }
 }
 
@@ -215,12 +216,11 @@ extern "C" int64_t lgcn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
   return lgcn_align_up(4 * n_nodes, 256) + lgcn_align_up(4 * n_edges, 256) + 4352 + 256;
 }
 
-extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len,
-                              int n_keys, int64_t n_nodes, int32_t* rowptr, int32_t* col, void* workspace,
-                              int32_t* err_flag, void* stream) {
+static int csr_build_impl(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len, int n_keys,
+                          int64_t n_nodes, int64_t n_src, int plain, int32_t* rowptr, int32_t* col, void* workspace,
+                          int32_t* err_flag, cudaStream_t st) {
   LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "csr_build: n_keys %d out of range", n_keys);
-  LGCN_CHECK_ARG(n_nodes >= 0, "csr_build: n_nodes < 0");
-  cudaStream_t st = (cudaStream_t)stream;
+  LGCN_CHECK_ARG(n_nodes >= 0 && n_src >= 0, "csr_build: negative size");
   EdgeSets es;
   es.n_keys = n_keys;
   es.start[0] = 0;
@@ -232,7 +232,7 @@ extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h
   }
   const int64_t E = es.start[n_keys];
   LGCN_CHECK_ARG(E < (int64_t)1 << 31, "csr_build: %lld edges exceed int32", (long long)E);
-  LGCN_CHECK_ARG(n_nodes * (int64_t)(n_keys + 1) < (int64_t)1 << 31, "csr_build: block index exceeds int32");
+  LGCN_CHECK_ARG(n_src * (int64_t)(plain ? 1 : n_keys + 1) < (int64_t)1 << 31, "csr_build: block index exceeds int32");
   int32_t* cnt = (int32_t*)workspace;
   int32_t* slot_edge = (int32_t*)((char*)workspace + lgcn_align_up(4 * n_nodes, 256));
   int32_t* scan_scratch = (int32_t*)((char*)slot_edge + lgcn_align_up(4 * E, 256));
@@ -240,16 +240,30 @@ extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h
   LGCN_CUDA_OK(cudaMemsetAsync(err_flag, 0, 4, st));
   const unsigned eb = E ? min(lgcn_cdiv(E, 256), 148u * 16u) : 0u;
   if (eb) {
-    k_csr_hist<<<eb, 256, 0, st>>>(es, n_nodes, cnt, err_flag);
+    k_csr_hist<<<eb, 256, 0, st>>>(es, n_nodes, n_src, cnt, err_flag);
     LGCN_LAUNCH_OK();
   }
   if (lgcn_launch_exclusive_scan(cnt, rowptr, n_nodes, scan_scratch, st)) return -2;
   if (eb) {
     LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_nodes, st));
-    k_csr_place<<<eb, 256, 0, st>>>(es, n_nodes, rowptr, cnt, slot_edge);
+    k_csr_place<<<eb, 256, 0, st>>>(es, n_nodes, n_src, rowptr, cnt, slot_edge);
     LGCN_LAUNCH_OK();
-    k_csr_finish<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(es, n_nodes, rowptr, slot_edge, col);
+    k_csr_finish<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(es, n_nodes, plain, rowptr, slot_edge, col);
     LGCN_LAUNCH_OK();
   }
   return 0;
+}
+
+extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len,
+                              int n_keys, int64_t n_nodes, int32_t* rowptr, int32_t* col, void* workspace,
+                              int32_t* err_flag, void* stream) {
+  return csr_build_impl(h_u, h_v, h_len, n_keys, n_nodes, n_nodes, 0, rowptr, col, workspace, err_flag, (cudaStream_t)stream);
+}
+
+extern "C" int lgcn_scatter_csr_build(const int64_t* dst, const int64_t* src, int64_t n_edges, int64_t n_dst,
+                                      int64_t n_src, int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag,
+                                      void* stream) {
+  const int64_t* u[1] = {dst};
+  const int64_t* v[1] = {src};
+  return csr_build_impl(u, v, &n_edges, 1, n_dst, n_src, 1, rowptr, col, workspace, err_flag, (cudaStream_t)stream);
 }

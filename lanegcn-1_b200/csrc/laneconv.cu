@@ -67,6 +67,17 @@ extern "C" int lgcn_laneconv_gather_gn_relu(const float* Y, int n_blocks, const 
   return 0;
 }
 
+extern "C" int lgcn_gather_rows_gn_relu(const float* base, int64_t base_ld, const float* blocks, const int32_t* rowptr,
+                                        const int32_t* col, const float* gamma, const float* beta, float* out,
+                                        int64_t n_rows, void* stream) {
+  LGCN_CHECK_ARG(base_ld >= LGCN_C && base_ld % 4 == 0, "gather_rows: bad base_ld %lld", (long long)base_ld);
+  if (n_rows <= 0) return 0;
+  k_gather_gn_relu<false><<<lgcn_cdiv(n_rows, GATHER_WARPS), GATHER_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      base, base_ld, blocks, rowptr, col, gamma, beta, out, n_rows);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int lgcn_segsum_gn_relu(const float* a, const float* c, const int32_t* rowptr, const float* gamma,
                                    const float* beta, float* out, int64_t n_rows, void* stream) {
   if (n_rows <= 0) return 0;

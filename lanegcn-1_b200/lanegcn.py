@@ -184,15 +184,18 @@ def _packed_of(graph: dict) -> PackedGraph:
     if pg is not None:
         return pg
     feats = graph["feats"]
+    if not torch.is_tensor(feats):  # LaneRCNN sub-graph dicts keep per-scene lists (lanercnn.py:192-197)
+        feats = feats.cat if getattr(feats, "cat", None) is not None else torch.cat(list(feats), 0)
     _need_cuda(feats, "graph['feats']")
     n = feats.shape[0]
     pg = build_csr(_edge_sets_of(graph), n, feats.device)
     pg.feats = _f32c(feats)
     pg.ctrs = _as_scene_list(graph["ctrs"])
-    pg.meta = torch.empty(n, 4, dtype=torch.float32, device=feats.device)
-    _C.check(_C.lib().lgcn_pack_meta(_f32c(graph["turn"]).data_ptr(), _f32c(graph["control"]).data_ptr(),
-                                     _f32c(graph["intersect"]).data_ptr(), pg.meta.data_ptr(), n,
-                                     _C.stream_ptr()), "pack_meta")
+    if "turn" in graph:  # only A2M.meta reads it
+        pg.meta = torch.empty(n, 4, dtype=torch.float32, device=feats.device)
+        _C.check(_C.lib().lgcn_pack_meta(_f32c(graph["turn"]).data_ptr(), _f32c(graph["control"]).data_ptr(),
+                                         _f32c(graph["intersect"]).data_ptr(), pg.meta.data_ptr(), n,
+                                         _C.stream_ptr()), "pack_meta")
     graph["_packed"] = pg
     return pg
 

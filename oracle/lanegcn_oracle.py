@@ -293,3 +293,71 @@ def lane_roi(sd, prefix: str, feat: Tensor, graph: dict) -> Tensor:
 def global_graph_net(sd, prefix: str, feat: Tensor, graph: dict) -> Tensor:
     """lanercnn.py:552-600 — identical to the M2M loop."""
     return lane_conv_stack(sd, prefix, feat, graph)
+
+
+def rcnn_graph_gather(graphs: List[dict]) -> dict:
+    """lanercnn.py:234-277: LaneGCN's graph_gather + num_nodes / counts / pose (= ctrs | feats per scene)."""
+    g = graph_gather(graphs)
+    g["num_nodes"] = [x["num_nodes"] for x in graphs]
+    g["pose"] = [torch.cat([x["ctrs"], x["feats"]], -1) for x in graphs]
+    return g
+
+
+def rcnn_subgraph_gather(subgraphs_in_batch) -> dict:
+    """lanercnn.py:122-231 (the keys the forward graph layers read)."""
+    flat = [sg for sgs in subgraphs_in_batch for sg in sgs]
+    counts, c = [], 0
+    for sg in flat:
+        counts.append(c)
+        c += len(sg["feats"])
+    g = {"num_nodes": c, "counts": counts}
+    per_scene = lambda f: [torch.cat([f(sg) for sg in sgs], 0) for sgs in subgraphs_in_batch]  # noqa: E731
+    g["feats"] = per_scene(lambda sg: sg["feats"])
+    g["agent_feat"] = per_scene(lambda sg: sg["agent_feat"].view(1, -1))
+    g["ctrs"] = [f[:, :2] for f in g["feats"]]
+    g["pose"] = [f[:, :4] for f in g["feats"]]
+    g["a2m"] = {"u": torch.cat([sg["a2m"]["u"].long() + i for i, sg in enumerate(flat)]),
+                "v": torch.cat([sg["a2m"]["v"].long() + counts[i] for i, sg in enumerate(flat)])}
+
+    def cat_edges(get):
+        parts = [get(sg).long() + counts[i] for i, sg in enumerate(flat) if len(get(sg)) > 0]
+        return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.long)
+
+    for k1 in ("pre", "suc"):
+        g[k1] = [{k2: cat_edges(lambda sg, i=i, k2=k2: sg[k1][i][k2]) for k2 in ("u", "v")} for i in range(6)]
+    for k1 in ("left", "right"):
+        g[k1] = {k2: cat_edges(lambda sg, k2=k2: sg[k1][k2]) for k2 in ("u", "v")}
+    return g
+
+
+def lane_input(sd, p: str, graph: dict) -> Tensor:
+    """lanercnn.py:309-351."""
+    m = F.linear(torch.cat(graph["feats"], 0), sd[p + ".map_fc.weight"])
+    a = torch.cat(graph["agent_feat"], 0)
+    m.index_add_(0, graph["a2m"]["v"], F.linear(a[graph["a2m"]["u"]], sd[p + ".agt_fc.weight"]))
+    return F.relu(gn(m, sd, p + ".bn"))
+
+
+def lane_pooling(sd, p: str, context_feat, context_graph, target_feat, target_graph, dist_th=6.0) -> Tensor:
+    """lanercnn.py:463-514 (pairs on centres, relative 4-D pose feature, scatter on the target index wi)."""
+    hi, wi = att_pairs(context_graph["ctrs"], target_graph["ctrs"], [len(x) for x in context_graph["ctrs"]],
+                       [len(x) for x in target_graph["ctrs"]], dist_th)
+    cp, tp = torch.cat(context_graph["pose"], 0), torch.cat(target_graph["pose"], 0)
+    d = F.relu(F.linear(cp[hi] - tp[wi], sd[p + ".relpose.0.weight"], sd[p + ".relpose.0.bias"]))
+    c = linear_gn(torch.cat([context_feat[hi], d], -1), sd, p + ".ctx.0", act=True)
+    c = F.linear(c, sd[p + ".ctx.1.weight"])
+    t = F.linear(target_feat, sd[p + ".input.weight"])
+    t.index_add_(0, wi, c)
+    t = F.relu(gn(t, sd, p + ".norm"))
+    t = linear_gn(t, sd, p + ".mlp.0", act=True)
+    t = linear_gn(t, sd, p + ".mlp.1", act=False)
+    return F.relu(t + target_feat)
+
+
+def interactor(sd, p: str, graph: dict, subgraph: dict, roi_feat: Tensor) -> Tensor:
+    """lanercnn.py:630-642."""
+    g_in = _mlp2(torch.cat(graph["ctrs"], 0), sd, p + ".input", act=False)
+    g_in = F.relu(g_in + _mlp2(graph["feats"], sd, p + ".seg", act=False))
+    g_feat = lane_pooling(sd, p + ".roi2graph", roi_feat, subgraph, g_in, graph)
+    g_feat = lane_conv_stack(sd, p + ".global_graph_net", g_feat, graph)
+    return lane_pooling(sd, p + ".graph2roi", g_feat, graph, roi_feat, subgraph)
