@@ -265,3 +265,32 @@ class Interactor(nn.Module):
         graph_feat = self.roi2graph(roi_feat, subgraph, g_in, graph)
         graph_feat = self.global_graph_net(graph_feat, graph)
         return self.graph2roi(graph_feat, graph, roi_feat, subgraph)
+
+
+class Net(nn.Module):
+    """The forward GRAPH path of lanercnn.Net (lanercnn.py:85-119) up to the RoI features that ``Decode`` consumes:
+    graph_gather / subgraph_gather -> LaneInput -> LaneRoI -> Interactor -> LaneRoI.  Sub-module names follow the
+    reference (``input``, ``roi_net1``, ``interactor``, ``roi_net2``) so its checkpoints load by key with
+    ``strict=False``; ``Decode`` (python NMS + polynomial trajectory sampling) is outside the graph path."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.input = LaneInput(config)
+        self.roi_net1 = LaneRoI(config, input_dim=config["n_map"])
+        self.interactor = Interactor(config)
+        self.roi_net2 = LaneRoI(config, input_dim=config["n_map"])
+
+    @torch.no_grad()
+    def forward(self, data: Dict):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("lanegcn_b200: move the model to a CUDA device first (there is no CPU path)")
+        with torch.cuda.device(dev):
+            graph = graph_gather(data["graph"])
+            roi = subgraph_gather(data["subgraphs"], dev)
+            feat = self.input(roi)
+            feat = self.roi_net1(feat, roi)
+            feat = self.interactor(graph, roi, feat)
+            feat = self.roi_net2(feat, roi)
+            return {"roi_feat": feat, "graph": graph, "graphRoI": roi}

@@ -115,3 +115,24 @@ def test_roi_dropins_match_reference_golden(cuda, lib):
     assert_close(mods["pool"](roi_feat.to(cuda), roi, g_feat.to(cuda), graph), fx["out_pool_r2g"], "LanePooling roi->graph")
     assert_close(mods["pool"](g_feat.to(cuda), graph, roi_feat.to(cuda), roi), fx["out_pool_g2r"], "LanePooling graph->roi")
     assert_close(mods["inter"](graph, roi, roi_feat.to(cuda)), fx["out_interactor"], "Interactor")
+
+
+@pytest.mark.gpu
+def test_lanercnn_graph_path_end_to_end_vs_oracle(cuda, lib):
+    """BASELINE config 5: LaneRCNN's forward graph layers chained (input -> roi_net1 -> interactor -> roi_net2) on
+    synthetic scenes, against the oracle composition of the same reference call sites (lanercnn.py:97-112)."""
+    net = R.Net(L.config)
+    shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.seeded_state_dict(shapes, 9)
+    net.load_state_dict(sd)
+    net = net.to(cuda).eval()
+    batch = synth.collate(roi_scenes())
+    graph = O.rcnn_graph_gather(O.to_long(batch["graph"]))
+    roi = O.rcnn_subgraph_gather(O.to_long(batch["subgraphs"]))
+    with torch.no_grad():
+        f = O.lane_input(sd, "input", roi)
+        f = O.lane_roi(sd, "roi_net1", f, roi)
+        f = O.interactor(sd, "interactor", graph, roi, f)
+        want = O.lane_roi(sd, "roi_net2", f, roi)
+    got = net(synth.collate(roi_scenes()))["roi_feat"]
+    assert_close(got, want, "LaneRCNN roi_feat")
