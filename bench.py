@@ -268,6 +268,19 @@ def run_ours(args):
             traffic = tj.get("dram_bytes_per_launch")
     step_kernel_ms = {k: round(ms_kind[i] / args.steps, 4) for i, k in enumerate(["wide_gemm", "gather", "ctr2", "att"])}
 
+    # second roofline: the wide projection GEMM (tensor-bound; 3xTF32 executes 3 tf32 MMAs per useful fp32 MAC)
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = float(json.load(open(pk))["bf16_tflops_sustained"]) if os.path.exists(pk) else 1400.0
+    wide_ms = ms_kind[0] / max(1, n_kind[0])
+    useful_tf = 2.0 * n_nodes * 128 * 1920 / (wide_ms * 1e-3) / 1e12 if wide_ms > 0 else 0.0
+    roof_gemm = {"kernel": "k_wide_tc (LaneConv wide projection [N,128]x[128,1920], tcgen05 3xTF32)", "bound": "tensor",
+                 "achieved": round(3 * useful_tf, 1), "peak": round(bf16 / 2, 1), "unit": "TFLOP/s",
+                 "frac": round(3 * useful_tf / (bf16 / 2), 4), "useful_fp32_tflops": round(useful_tf, 1),
+                 "avg_launch_ms": round(wide_ms, 5), "launches_timed": int(n_kind[0]),
+                 "peak_source": "tf32 dense peak taken as half of MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, "
+                                "kernel timed inside a long step); executed flops = 3 x 2*N*128*1920",
+                 "hbm_floor_ms": round((512 + 7680) * n_nodes / (peak * 1e9) * 1e3, 4)}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, ms, cores = cpu_forward_rate(3, 1)
@@ -297,6 +310,7 @@ def run_ours(args):
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": round(gather_ms, 5),
                      "launches_timed": int(n_kind[1])},
+        "roofline_gemm": roof_gemm,
         "clocks": clk,
     }
     if cpu:

@@ -264,6 +264,7 @@ class StagedGraphs:
         self.off: List[int] = [0]
         self.num_scales = 0
         self.fl = self.local = self.segs = self.off_dev = None
+        self.extra_float = self.extra_i32 = self.extra_i64 = None
         self.seg_len: List[int] = []
         self.h2d_bytes = 0
 
@@ -275,41 +276,57 @@ def _edge_names(num_scales: int):
     return names + [("left", None), ("right", None)]
 
 
-def stage_graphs(graphs: List[dict]) -> StagedGraphs:
-    """Host side of graph_gather: concatenate the per-scene arrays into three staging buffers and issue one
-    H2D copy each (replaces ~38 cudaMemcpyAsync + 33 int16->int64 casts PER SCENE, utils.py:74-96)."""
+def stage_graphs(graphs: List[dict], extra_float: Optional[List[Tensor]] = None,
+                 extra_i32: Optional[List[int]] = None, extra_i64: Optional[List[int]] = None) -> StagedGraphs:
+    """Host side of graph_gather: pack the per-scene arrays into FOUR staging buffers (floats, scene-local edge
+    indices, an int64 table, an int32 table) and issue one H2D copy each (replaces ~38 cudaMemcpyAsync + 33
+    int16->int64 casts PER SCENE, utils.py:74-96).  ``extra_*`` ride along in the same buffers (Net.stage puts the
+    actor tensors there) and come back as ``sg.extra_float`` / ``sg.extra_i32`` / ``sg.extra_i64``."""
     sg = StagedGraphs()
+    B = len(graphs)
     sg.sizes = [int(g["num_nodes"]) for g in graphs]
     for n in sg.sizes:
         sg.off.append(sg.off[-1] + n)
+    N = sg.off[-1]
     sg.num_scales = len(graphs[0]["pre"])
     dev = _target_device(graphs[0]["feats"])
     parts = []
     for key in ("ctrs", "feats", "turn", "control", "intersect"):
         parts += [g[key].reshape(-1) for g in graphs]
-    sg.fl = _stage_cat(parts, dev, torch.float32, "graph_fl")
-    locs, seg_add = [], []
-    for k1, s in _edge_names(sg.num_scales):
+    n_extra = len(extra_float) if extra_float else 0
+    if n_extra:
+        parts += extra_float
+    fl, fl_sizes = _stage_cat(parts, dev, torch.float32, "graph_fl")
+    sg.fl = fl[: 8 * N]
+    sg.extra_float = fl[8 * N:]
+    locs = []
+    names = _edge_names(sg.num_scales)
+    for k1, s in names:
+        src = [g[k1] for g in graphs] if s is None else [g[k1][s] for g in graphs]
         for k2 in ("u", "v"):
-            for j, g in enumerate(graphs):
-                t = g[k1][k2] if s is None else g[k1][s][k2]
-                if t.dim() == 0:  # pickles where an empty array collapsed to a scalar (lanegcn.py:204-207)
-                    t = t.new_zeros(0)
-                locs.append(t)
-                seg_add.append(sg.off[j])
-    sg.seg_len = [t.numel() for t in locs]
+            locs += [d[k2] for d in src]
+    if any(t.dim() == 0 for t in locs[-4 * B:]):  # pickles where an empty left/right array collapsed to a scalar
+        locs = [t.new_zeros(0) if t.dim() == 0 else t for t in locs]                   # (lanegcn.py:204-207)
     dt = locs[0].dtype
-    if any(t.dtype != dt for t in locs):
+    if {t.dtype for t in locs} != {dt}:
         dt, locs = torch.int64, [t.long() for t in locs]
     if dt not in (torch.int16, torch.int32, torch.int64):
         raise RuntimeError(f"lanegcn_b200: edge indices must be int16/int32/int64, got {dt}")
-    sg.local = _stage_cat(locs, dev, dt, "graph_idx")
-    seg_start = [0]
-    for n in sg.seg_len:
-        seg_start.append(seg_start[-1] + n)
-    sg.segs = _stage(torch.tensor(seg_start + seg_add, dtype=torch.int64), dev, torch.int64, "segs")
-    sg.off_dev = _stage(torch.tensor(sg.off, dtype=torch.int32), dev, torch.int32, "off")
-    sg.h2d_bytes = sum(t.numel() * t.element_size() for t in (sg.fl, sg.local, sg.segs, sg.off_dev))
+    sg.local, loc_bytes = _stage_cat(locs, dev, dt, "graph_idx")
+    seg_len = loc_bytes // sg.local.element_size()
+    sg.seg_len = seg_len.tolist()
+    n_seg = len(locs)
+    table = np.empty(2 * n_seg + 1 + (len(extra_i64) if extra_i64 else 0), np.int64)
+    table[0] = 0
+    np.cumsum(seg_len, out=table[1: n_seg + 1])
+    table[n_seg + 1: 2 * n_seg + 1] = np.tile(np.asarray(sg.off[:-1], np.int64), 2 * len(names))
+    if extra_i64:
+        table[2 * n_seg + 1:] = extra_i64
+    t64 = _stage(torch.from_numpy(table), dev, torch.int64, "tab64")
+    sg.segs, sg.extra_i64 = t64[: 2 * n_seg + 1], t64[2 * n_seg + 1:]
+    t32 = _stage(torch.tensor(sg.off + (extra_i32 or []), dtype=torch.int32), dev, torch.int32, "tab32")
+    sg.off_dev, sg.extra_i32 = t32[: B + 1], t32[B + 1:]
+    sg.h2d_bytes = sum(t.numel() * t.element_size() for t in (fl, sg.local, t64, t32))
     return sg
 
 
@@ -390,10 +407,11 @@ class _PinnedPool:
 
 
 def _stage_cat(parts: List[Tensor], dev, dtype, tag: str) -> Tensor:
-    """Concatenate 1-D CPU tensors straight into a pinned buffer and issue ONE async H2D copy.
-    Device inputs are concatenated on the device."""
+    """Concatenate 1-D CPU tensors straight into a pinned buffer and issue ONE async H2D copy; returns the device
+    tensor and the per-part byte sizes.  Device inputs are concatenated on the device."""
     if parts[0].is_cuda:
-        return torch.cat([p.to(dtype) for p in parts])
+        out = torch.cat([p.to(dtype).reshape(-1) for p in parts])
+        return out, np.fromiter((p.numel() * out.element_size() for p in parts), np.int64, len(parts))
     if {p.dtype for p in parts} != {dtype} or not all(p.is_contiguous() for p in parts):
         parts = [p.to(dtype).contiguous() for p in parts]
     k = len(parts)
@@ -410,7 +428,7 @@ def _stage_cat(parts: List[Tensor], dev, dtype, tag: str) -> Tensor:
     ev = torch.cuda.Event()
     ev.record()
     ring["evs"][i] = ev
-    return out
+    return out, sizes
 
 
 def _stage(t: Tensor, dev, dtype, tag: str = "misc") -> Tensor:
@@ -418,7 +436,7 @@ def _stage(t: Tensor, dev, dtype, tag: str = "misc") -> Tensor:
     if t.is_cuda:
         return t.to(dtype).contiguous()
     shape = t.shape
-    return _stage_cat([t.reshape(-1)], dev, dtype, tag + str(dtype)).view(shape)
+    return _stage_cat([t.reshape(-1)], dev, dtype, tag + str(dtype))[0].view(shape)
 
 
 # --------------------------------------------------------------------------- Att pair lists
@@ -782,6 +800,7 @@ class DeviceBatch:
         self.graphs = None       # StagedGraphs
         self.rot = None          # f32 [B,2,2]
         self.orig = None         # f32 [B,2]
+        self.ready = None        # event: the staging copies (issued on the copy stream) have completed
         self.rot_a = None        # f32 [sum A,2,2]  the scene's rot, per actor
         self.orig_a = None       # f32 [sum A,2]
         self.h2d_bytes = 0
@@ -816,27 +835,42 @@ class Net(nn.Module):
         return dev
 
     def stage(self, data: Dict) -> DeviceBatch:
-        """Host packing + H2D of one collated batch (what utils.gpu does tensor by tensor, utils.py:74-85)."""
+        """Host packing + H2D of one collated batch (what utils.gpu does tensor by tensor, utils.py:74-85): every
+        float of the batch travels in ONE pinned arena, the edge indices in a second, two small integer tables."""
         dev = self._device()
-        with torch.cuda.device(dev):
+        # everything below runs on a dedicated copy stream, so the H2D transfers of batch i+1 overlap the kernels
+        # of batch i (prefetch_forward); forward_device waits for b.ready before touching the staged tensors
+        with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev, "copy")):
             b = DeviceBatch()
             sizes = [len(x) for x in data["feats"]]
-            b.actors = _stage(torch.cat(list(data["feats"]), 0), dev, torch.float32, "actors")
-            b.actor_ctrs = scene_list(_stage(torch.cat(list(data["ctrs"]), 0), dev, torch.float32, "actr"), sizes)
-            rot, orig = torch.stack(list(data["rot"])), torch.stack(list(data["orig"]))
-            b.rot = _stage(rot, dev, torch.float32, "rot")
-            b.orig = _stage(orig, dev, torch.float32, "orig")
-            if rot.is_cuda:
+            A, B = sum(sizes), len(sizes)
+            aoff = [0]
+            for n in sizes:
+                aoff.append(aoff[-1] + n)
+            if data["feats"][0].is_cuda:  # already on the device: no staging to do for the actor side
+                sg = stage_graphs(data["graph"])
+                b.actors = torch.cat(list(data["feats"]), 0).float()
+                ctrs = torch.cat(list(data["ctrs"]), 0).float()
+                b.rot, b.orig = torch.stack(list(data["rot"])).float(), torch.stack(list(data["orig"])).float()
                 cnt = torch.tensor(sizes, device=dev)
-                b.rot_a, b.orig_a = torch.repeat_interleave(b.rot, cnt, 0), torch.repeat_interleave(b.orig, cnt, 0)
-            else:  # expand per actor on the host and stage through pinned memory: a pageable H2D copy here would
-                #    block the host behind all queued device work and serialise prefetch_forward
-                cnt = torch.tensor(sizes)
-                b.rot_a = _stage(torch.repeat_interleave(rot.float(), cnt, 0), dev, torch.float32, "rot_a")
-                b.orig_a = _stage(torch.repeat_interleave(orig.float(), cnt, 0), dev, torch.float32, "orig_a")
-            b.graphs = stage_graphs(data["graph"])
-            b.h2d_bytes = b.graphs.h2d_bytes + 4 * (b.actors.numel() + b.actor_ctrs.cat.numel() + b.rot.numel()
-                                                    + b.orig.numel() + b.rot_a.numel() + b.orig_a.numel()) + 12 * (len(sizes) + 1)
+                off_dev = torch.tensor(aoff, dtype=torch.int32, device=dev)
+            else:
+                extra = ([x.reshape(-1) for x in data["feats"]] + [x.reshape(-1) for x in data["ctrs"]]
+                         + [x.reshape(-1) for x in data["rot"]] + [x.reshape(-1) for x in data["orig"]])
+                sg = stage_graphs(data["graph"], extra_float=extra, extra_i32=aoff, extra_i64=sizes)
+                fl = sg.extra_float
+                b.actors = fl[: 60 * A].view(A, 20, 3)
+                ctrs = fl[60 * A: 62 * A].view(A, 2)
+                b.rot = fl[62 * A: 62 * A + 4 * B].view(B, 2, 2)
+                b.orig = fl[62 * A + 4 * B: 62 * A + 6 * B].view(B, 2)
+                cnt, off_dev = sg.extra_i64, sg.extra_i32
+            b.actor_ctrs = scene_list(ctrs, sizes, off_dev)
+            b.rot_a = torch.repeat_interleave(b.rot, cnt, 0, output_size=A)     # the scene's rot / orig per actor
+            b.orig_a = torch.repeat_interleave(b.orig, cnt, 0, output_size=A)
+            b.graphs = sg
+            b.h2d_bytes = sg.h2d_bytes
+            b.ready = torch.cuda.Event()
+            b.ready.record()
             return b
 
     @torch.no_grad()
@@ -847,6 +881,12 @@ class Net(nn.Module):
     def forward_device(self, b: DeviceBatch) -> Dict[str, List[Tensor]]:
         cfg = self.config
         with torch.cuda.device(b.actors.device):
+            cur = torch.cuda.current_stream()
+            if b.ready is not None:
+                cur.wait_event(b.ready)
+                for t in (b.graphs.fl, b.graphs.local, b.graphs.segs, b.graphs.off_dev, b.actors, b.rot_a, b.orig_a,
+                          b.actor_ctrs.cat, b.actor_ctrs.off_dev):
+                    t.record_stream(cur)  # allocated on the copy stream, consumed here
             actor_ctrs = b.actor_ctrs
             sizes = [len(x) for x in actor_ctrs]
             actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev)
