@@ -31,7 +31,10 @@
 //               epilogue is an L2 round trip: two warps per scheduler hide each other's latency, the residual
 //               is prefetched before the GroupNorm exchange, gamma/beta live in shared memory.  GroupNorm(1)
 //               statistics: each half computes (mean, M2) of its 64 values, the two halves are combined with
-//               Chan's formula through shared memory (two 64-thread named barriers).  Results are staged as
+//               Chan's formula through shared memory (two 64-thread named barriers).  (Tried and rejected: two
+//               teams of four warps alternating accumulator stages with each thread owning a full row re-read
+//               from TMEM in two passes — correct, but 127 us instead of 109 us per ctr2 launch: TMEM->register
+//               reads are bandwidth-limited, so every accumulator value should be read exactly once.)  Results are staged as
 //               32x32 fp32 blocks in swizzled shared memory and written with TMA bulk tensor stores (coalesced
 //               128 B rows; rows >= M clipped by the tensor map).
 #include "tc_common.cuh"
