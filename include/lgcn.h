@@ -182,6 +182,19 @@ int64_t lgcn_laneconv_workspace_bytes(int64_t n_nodes, int n_keys);
 int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int32_t* col, int n_keys, int n_blocks,
                         const float* wpack, int64_t n_nodes, void* workspace, void* stream);
 
+/* The same stack, aggregate-first: each block is ONE tcgen05 kernel that gathers the neighbour rows of feat straight
+ * into the GEMM operand (sum_k W_k . sum_{e in key k} feat[src(e)]), so the [n_nodes, (K+1)*128] projection is never
+ * written to memory; ctr2 + GroupNorm + residual + ReLU run in the same kernel.  The plan is static per graph
+ * (built from the merged CSR of lgcn_csr_build; n_edges = its entry count) and shared by every block and by
+ * MapNet and M2M.  Same wpack, same result up to fp32 summation order.  tcgen05 engine only.
+ * plan: lgcn_laneconv_plan_bytes; workspace: lgcn_laneconv_planned_workspace_bytes.                          */
+int64_t lgcn_laneconv_plan_bytes(int64_t n_nodes, int64_t n_edges, int n_keys);
+int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes,
+                             int64_t n_edges, void* plan, void* stream);
+int64_t lgcn_laneconv_planned_workspace_bytes(int64_t n_nodes, int64_t n_edges, int n_keys);
+int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_edges, int n_keys, int n_blocks,
+                                const float* wpack, int64_t n_nodes, void* workspace, void* stream);
+
 /* One Att layer (lanegcn.py:662-710) on a prebuilt pair list.  wpack, contiguous fp32:
  *   dist.0.weight[128,2] | dist.0.bias[128] | dist.2.linear.weight[128,128] | dist.2.norm.{weight,bias}
  *   | query.linear.weight[128,128] | query.norm.{w,b} | ctx.0.linear.weight[128,384] | ctx.0.norm.{w,b}

@@ -51,6 +51,10 @@ _SIGS = {
     "lgcn_laneconv_wpack_floats": (_i64, [_i32]),
     "lgcn_laneconv_workspace_bytes": (_i64, [_i64, _i32]),
     "lgcn_laneconv_stack": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "lgcn_laneconv_plan_bytes": (_i64, [_i64, _i64, _i32]),
+    "lgcn_laneconv_plan_build": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp]),
+    "lgcn_laneconv_planned_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "lgcn_laneconv_stack_planned": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
     "lgcn_att_wpack_floats": (_i64, []),
     "lgcn_att_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_att_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),

@@ -194,6 +194,49 @@ extern "C" int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int
   return 0;
 }
 
+// Planned (aggregate-first) stack: every block is ONE kernel (laneconv_fused.cu); the features ping-pong between
+// `feat` and a workspace buffer because a block reads neighbour rows while other tiles already write theirs.
+extern "C" int64_t lgcn_laneconv_planned_workspace_bytes(int64_t n_nodes, int64_t n_edges, int n_keys) {
+#if LGCN_HAVE_TC
+  return lgcn_align_up(n_nodes * LGCN_C * 4, 1024) + lgcn_laneconv_fused_aux_bytes(n_edges) +
+         2 * lgcn_align_up((int64_t)(n_keys + 2) * CC * 4, 1024) + 1024;
+#else
+  (void)n_nodes; (void)n_edges; (void)n_keys;
+  return 0;
+#endif
+}
+
+extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_edges, int n_keys, int n_blocks,
+                                           const float* wpack, int64_t n_nodes, void* workspace, void* stream) {
+#if LGCN_HAVE_TC
+  LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "laneconv_stack_planned: n_keys %d", n_keys);
+  LGCN_CHECK_ARG(feat && plan && wpack && workspace, "laneconv_stack_planned: NULL argument");
+  LGCN_CHECK_ARG(lgcn_get_gemm_engine() == 1, "laneconv_stack_planned needs the tcgen05 engine");
+  if (n_nodes <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = n_keys + 1;
+  float* other = (float*)workspace;
+  float* xa = (float*)((char*)other + lgcn_align_up(n_nodes * LGCN_C * 4, 1024));
+  float* w_hi = (float*)((char*)xa + lgcn_laneconv_fused_aux_bytes(n_edges));
+  float* w_lo = (float*)((char*)w_hi + lgcn_align_up((int64_t)(nb + 1) * CC * 4, 1024));
+  for (int i = 0; i < n_blocks; ++i) {
+    const float* w = wpack + (int64_t)i * lgcn_laneconv_wpack_floats(n_keys);   // Wcat | Wctr2 | 4 norm vectors
+    const float* gn = w + (int64_t)(nb + 1) * CC;
+    const float* src = (i & 1) ? other : feat;
+    float* dst = (i & 1) ? feat : other;
+    if (int rc = lgcn_split_tf32(w, w_hi, w_lo, (int64_t)(nb + 1) * CC, st)) return rc;
+    LgcnProfScope ps(LGCN_PROF_WIDE, st);
+    if (int rc = lgcn_launch_laneconv_fused(src, dst, plan, n_nodes, n_edges, n_keys, w_hi, w_lo, gn, xa, 1, st)) return rc;
+  }
+  if (n_blocks & 1) LGCN_CUDA_OK(cudaMemcpyAsync(feat, other, n_nodes * LGCN_C * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+#else
+  (void)feat; (void)plan; (void)n_edges; (void)n_keys; (void)n_blocks; (void)wpack; (void)n_nodes; (void)workspace; (void)stream;
+  LGCN_CHECK_ARG(false, "laneconv_stack_planned: built without the tcgen05 engine");
+  return -1;
+#endif
+}
+
 // ------------------------------------------------------------------ Att layer
 struct AttW {
   const float *d0w, *d0b, *d2w, *d2g, *d2b, *qw, *qg, *qb, *c0w, *c0g, *c0b, *c1w, *aw, *ng, *nb, *lw, *lg, *lb;

@@ -1,0 +1,573 @@
+// laneconv_fused.cu — one LaneConv block (lanegcn.py:331-362 = :448-479) as ONE tcgen05 kernel, aggregate-first:
+//
+//     out[n] = relu( GN( relu( GN( sum_k W_k . agg_k[n] ) ) . Wctr2^T ) + X[n] ),
+//     agg_0[n] = X[n] (ctr),   agg_k[n] = sum over edges e of key k with destination n of X[src(e)].
+//
+// The split path (gemm_tc_wide.cu + laneconv.cu) materialises Y = X . Wcat^T ([N, 1920] fp32: 1.49 GB written and
+// 1.31 GB gathered back per block at batch 128); here the neighbour rows of X are gathered straight into the A operand
+// and Y never exists: HBM traffic per block drops from ~3.2 GB to ~0.3 GB, the arithmetic (K = 15 x 128 per output
+// row, 3xTF32) is unchanged.  Sums are linear, so summing the source rows first and multiplying once per key is the
+// same map; the fp32 rounding differs from the reference's per-edge order at the 1e-7 level (parity tests hold both
+// paths to the same 1e-4 / 1e-5 tolerance against the oracle).
+//
+// Plan (static per graph, lgcn_laneconv_plan_build): tab[tile][key][128] = the ONE source row of (destination row,
+// key) (-1: none).  (row, key) pairs with several sources (3 % on lane graphs: merges, dilated scales) get an
+// auxiliary row: k_multi_sum writes XA[i] = sum of their sources (CSR order) before each block and tab holds -2-i,
+// so the hot loop has exactly one 64-byte load per thread and stage, with no data-dependent trip counts.
+//
+// Kernel: persistent, one CTA per SM, 128 destination rows per tile, 4 x (n_keys+1) [+4 for ctr2] stages per tile;
+// one stage = one 32-float K-chunk of one key:
+//   warp 0      TMA producer: W_k[:, 32 kc .. +32) hi | lo (pre-split tf32, 2 x 16 KB boxes) into a 5-stage ring
+//   warp 1      MMA issuer: A from TENSOR MEMORY (row -> lane, k -> column), B from the ring; per stage 4 k-steps x 3
+//               products (M=128, N=128, K=8): lo.hi + hi.lo -> cross accumulator, hi.hi -> main accumulator
+//   warps 4-11  A producers + epilogue.  Warp (q = w&3, h = w>>2 & 1) owns rows 32q..32q+31 (TMEM lane quarter) and
+//               floats [16h, 16h+16) of every chunk: 4 x 128-bit loads of the source row (prefetched two stages
+//               ahead), hi/lo split in registers, tcgen05.st into a 4-stage A ring in TMEM.  After the last key they
+//               drain the accumulators (columns [64h, 64h+64)), GroupNorm (Chan-combined with the partner warp) +
+//               ReLU, and feed the result back as the A operand of ctr2 (4 more stages, no trip through memory);
+//               then GroupNorm + residual + ReLU and TMA stores.
+//   TMEM        A ring 4 x (hi 32 | lo 32) = [0,256) | main [256,384) | cross [384,512)
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kWStages = 5;
+constexpr int kWStageBytes = 2 * 128 * 128;                  // hi 16 KB | lo 16 KB
+constexpr int kAStages = 4;
+constexpr int kSmemOut = kWStages * kWStageBytes;            // 160 KB: 8 x 4 KB store staging
+constexpr int kSmemGam = kSmemOut + 8 * 4096;                // gamma1 | beta1 | gamma2 | beta2 (4 x 512 B)
+constexpr int kSmemStat = kSmemGam + 4 * 512;                // float2 [2][128]
+constexpr int kSmemBar = kSmemStat + 2 * 128 * 8;
+constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kNumThreads = 384;
+constexpr int kMmaWarp = 1;
+constexpr uint32_t kIdesc = idesc_tf32(128, 128);
+constexpr uint32_t kColMain = 256, kColCross = 384;
+// The tensor core truncates the fp32 accumulator toward zero once per MMA instruction (-1.3e-8 relative each, see
+// gemm_tc.cu), so a 240-instruction hi.hi chain (15 keys x 16 k-steps) would carry a 3e-6 bias.  The main accumulator
+// is therefore flushed into registers (round-to-nearest fp32 adds) every kFlushKeys keys; the cross accumulator
+// holds values 2^-11 smaller and runs through.
+constexpr int kFlushKeys = 3;
+
+struct FusedArgs {
+  const float* X;        // [M,128] input features (also the residual)
+  const float* XA;       // auxiliary rows (multi-source sums)
+  const int32_t* tab;    // [n_tiles][n_keys][128]
+  const float* gn;       // gamma1 | beta1 | gamma2 | beta2
+  int64_t M;
+  int n_keys;
+  int chain;             // 1: ctr2 + GN + residual + ReLU inside the kernel
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
+                 const __grid_constant__ CUtensorMap whi_map, const __grid_constant__ CUtensorMap wlo_map) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  if (sbase & 1023u) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_w_full = sbase + kSmemBar;             // [5]
+  const uint32_t bar_w_empty = bar_w_full + 8 * kWStages;   // [5]
+  const uint32_t bar_a_full = bar_w_empty + 8 * kWStages;   // [4]
+  const uint32_t bar_a_empty = bar_a_full + 8 * kAStages;   // [4]
+  const uint32_t bar_acc_full = bar_a_empty + 8 * kAStages;
+  const uint32_t bar_acc_empty = bar_acc_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + 192);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(bar_a_full + 8 * i, 8);   // one arrive per producer warp
+      mbar_init(bar_a_empty + 8 * i, 1);
+    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 4 * 128; i += kNumThreads)
+    reinterpret_cast<float*>(smem + kSmemGam)[i] = a.gn[i];
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // scalars only below (a by-value struct captured by reference in a lambda ends up in local memory)
+  const int64_t M = a.M;
+  const float* __restrict__ X = a.X;
+  const float* __restrict__ XA = a.XA;
+  const int32_t* __restrict__ tab = a.tab;
+  const int n_keys = a.n_keys, nk = a.n_keys + 1;
+  const bool chain = a.chain != 0;
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+  const int64_t grid = gridDim.x;
+  const int keys_per_tile = nk + (chain ? 1 : 0);   // key nk = ctr2 (weights follow the projections in w_hi / w_lo)
+
+  if (warp == 0) {
+    // =========================================================== TMA producer: weight chunks
+    uint32_t phase = 0;
+    int ws = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
+      for (int kk = 0; kk < keys_per_tile; ++kk) {
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(bar_w_empty + 8 * ws, phase ^ 1);
+          if (elect_one()) {
+            const uint32_t bar = bar_w_full + 8 * ws, dst = sbase + ws * kWStageBytes;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWStageBytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&whi_map)), "r"(bar), "r"(kc * 32), "r"(kk * 128)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(dst + kWStageBytes / 2), "l"(reinterpret_cast<uint64_t>(&wlo_map)), "r"(bar), "r"(kc * 32), "r"(kk * 128)
+                : "memory");
+          }
+          __syncwarp();
+          if (++ws == kWStages) {
+            ws = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================================================== MMA issuer
+    uint32_t w_phase = 0, a_phase = 0, acc_uses = 0;
+    int ws = 0, as = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
+      for (int kk = 0; kk < keys_per_tile; ++kk) {
+        const bool fresh_all = kk == 0 || kk == nk;                         // projections / ctr2 start
+        const bool fresh_main = fresh_all || (kk < nk && kk % kFlushKeys == 0);   // main restarts after a flush
+        if (fresh_main) {
+          mbar_wait(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have read the accumulator(s)
+          ++acc_uses;
+        }
+        const bool publish = kk >= nk - 1 || (kk + 1) % kFlushKeys == 0;     // a flush / drain follows this key
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(bar_w_full + 8 * ws, w_phase);
+          mbar_wait(bar_a_full + 8 * as, a_phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_main = tmem_base + kColMain, d_cross = tmem_base + kColCross;
+            const uint32_t a_hi = tmem_base + as * 64, a_lo = a_hi + 32;
+            const uint32_t w_hi = sbase + ws * kWStageBytes, w_lo = w_hi + kWStageBytes / 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool k0 = kc == 0 && j == 0;
+              umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_all && k0) ? 0u : 1u);
+              umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
+              umma_tf32_ts(d_main, a_hi + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_main && k0) ? 0u : 1u);
+            }
+            umma_commit(bar_w_empty + 8 * ws);
+            umma_commit(bar_a_empty + 8 * as);
+            if (publish && kc == 3) umma_commit(bar_acc_full);
+          }
+          __syncwarp();
+          if (++ws == kWStages) {
+            ws = 0;
+            w_phase ^= 1;
+          }
+          if (++as == kAStages) {
+            as = 0;
+            a_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================================================== A producers + epilogue: warps 4..11
+    const int e = warp - 4, q = e & 3, h = e >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t my_buf = sbase + kSmemOut + e * 4096;
+    const uint32_t stat_mine = sbase + kSmemStat + (h * 128 + r) * 8, stat_other = sbase + kSmemStat + ((h ^ 1) * 128 + r) * 8;
+    const uint32_t gam = sbase + kSmemGam + h * 256;   // + 0: gamma1, + 512: beta1, + 1024: gamma2, + 1536: beta2
+
+    // ---- prefetch cursor: two stages ahead of the stage being converted
+    int64_t pt = blockIdx.x;
+    int pkk = 0, pkc = 0;
+    auto self_v = [&](int64_t t) -> int {
+      const int64_t m = t * kTileM + r;
+      return (t < n_tiles && m < M) ? (int)m : -1;
+    };
+    auto tab_v = [&](int64_t t, int kk) -> int {
+      return t < n_tiles ? __ldg(tab + ((t * n_keys + (kk - 1)) << 7) + r) : -1;
+    };
+    int pv = self_v(pt);
+    int pv_next = nk > 1 ? tab_v(pt, 1) : self_v(pt + grid);
+    float4 xq[2][4];
+    auto fetch = [&](float4(&dst)[4]) {
+      const float* p = pv >= 0 ? X + (int64_t)pv * LGCN_C : XA + (int64_t)(pv < -1 ? -2 - pv : 0) * LGCN_C;
+      const float4* s = reinterpret_cast<const float4*>(p + pkc * 32 + h * 16);
+      const bool live = pv != -1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = live ? __ldg(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (++pkc == 4) {   // next key: its table entry was requested four stages ago
+        pkc = 0;
+        pv = pv_next;
+        if (++pkk == nk) {
+          pkk = 0;
+          pt += grid;
+        }
+        int nkk = pkk + 1;
+        int64_t nt = pt;
+        if (nkk == nk) {
+          nkk = 0;
+          nt = pt + grid;
+        }
+        pv_next = nkk == 0 ? self_v(nt) : tab_v(nt, nkk);
+      }
+    };
+    uint32_t a_phase = 0, acc_uses = 0;
+    int as = 0;
+    // 16 floats -> hi/lo -> TMEM columns [c0, c0+16) (hi) and [c0+32, c0+48) (lo) of A stage `as`
+    auto put16 = [&](const float4(&x)[4], int c0) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float h0 = tf32_rna(x[c].x), h1 = tf32_rna(x[c].y), h2 = tf32_rna(x[c].z), h3 = tf32_rna(x[c].w);
+        hi[4 * c] = __float_as_uint(h0); lo[4 * c] = __float_as_uint(tf32_rna(x[c].x - h0));
+        hi[4 * c + 1] = __float_as_uint(h1); lo[4 * c + 1] = __float_as_uint(tf32_rna(x[c].y - h1));
+        hi[4 * c + 2] = __float_as_uint(h2); lo[4 * c + 2] = __float_as_uint(tf32_rna(x[c].z - h2));
+        hi[4 * c + 3] = __float_as_uint(h3); lo[4 * c + 3] = __float_as_uint(tf32_rna(x[c].w - h3));
+      }
+      TMEM_ST16(t_lane + as * 64 + c0, hi, 0);
+      TMEM_ST16(t_lane + as * 64 + 32 + c0, lo, 0);
+    };
+    auto stage_begin = [&]() {
+      mbar_wait(bar_a_empty + 8 * as, a_phase ^ 1);
+      tc_fence_after();
+    };
+    auto stage_end = [&]() {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full + 8 * as);
+      if (++as == kAStages) {
+        as = 0;
+        a_phase ^= 1;
+      }
+    };
+    // f[64] = columns [64h, 64h+64) of this thread's row: running fp32 sum of the flushed main accumulator
+    float f[64];
+    auto acc_wait = [&]() {
+      mbar_wait(bar_acc_full, acc_uses & 1);
+      ++acc_uses;
+      tc_fence_after();
+    };
+    auto acc_release = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty);
+    };
+    auto flush_main = [&]() {   // f += main; the MMA warp restarts main with accumulate = 0
+      acc_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[16];
+        TMEM_LD16(v, 0, t_lane + kColMain + h * 64 + g * 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) f[g * 16 + c] += __uint_as_float(v[c]);
+      }
+      acc_release();
+    };
+    auto drain_gn = [&](uint32_t gb, bool add) {   // gb: shared address of gamma (beta 512 B behind it) for this half
+      acc_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[16], x[16];
+        TMEM_LD16(v, 0, t_lane + kColMain + h * 64 + g * 16);
+        TMEM_LD16(x, 0, t_lane + kColCross + h * 64 + g * 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float y = __uint_as_float(v[c]) + __uint_as_float(x[c]);
+          f[g * 16 + c] = add ? f[g * 16 + c] + y : y;
+        }
+      }
+      acc_release();
+      float s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) s1 += f[c];
+      const float mean_h = s1 * (1.0f / 64.0f);
+      float m2_h = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float d = f[c] - mean_h;
+        m2_h = fmaf(d, d, m2_h);
+      }
+      st_shared_f2(stat_mine, mean_h, m2_h);
+      named_bar_sync(1 + q, 64);
+      const float2 o = ld_shared_f2(stat_other);
+      named_bar_sync(1 + q, 64);   // both halves have read: the slots may be rewritten by the next drain
+      const float mean = 0.5f * (mean_h + o.x);
+      const float dm = mean_h - o.x;
+      const float var = (m2_h + o.y + dm * dm * 32.0f) * (1.0f / 128.0f);
+      const float rstd = 1.0f / sqrtf(var + LGCN_GN_EPS);
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 g = ld_shared_f4(gb + c * 4), b = ld_shared_f4(gb + 512 + c * 4);
+        f[c] = fmaf((f[c] - mean) * rstd, g.x, b.x);
+        f[c + 1] = fmaf((f[c + 1] - mean) * rstd, g.y, b.y);
+        f[c + 2] = fmaf((f[c + 2] - mean) * rstd, g.z, b.z);
+        f[c + 3] = fmaf((f[c + 3] - mean) * rstd, g.w, b.w);
+      }
+    };
+    auto store_out = [&](int64_t m0) {   // f -> two 32 x 32 boxes through the 4 KB staging buffer
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_f4(my_buf + lane * 128 + ((c ^ (lane & 7)) << 4),
+                       make_float4(f[cb * 32 + 4 * c], f[cb * 32 + 4 * c + 1], f[cb * 32 + 4 * c + 2], f[cb * 32 + 4 * c + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&out_map)),
+                       "r"(my_buf), "r"(h * 64 + cb * 32), "r"((int32_t)(m0 + q * 32))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    };
+
+    fetch(xq[0]);
+    fetch(xq[1]);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
+      const int64_t m0 = t * kTileM;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) f[c] = 0.f;
+      for (int kk = 0; kk < nk; ++kk) {
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          stage_begin();
+          put16(xq[kc & 1], h * 16);
+          fetch(xq[kc & 1]);   // stage + 2
+          stage_end();
+          // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
+          // warp resumes
+          if (kc == 2 && kk > 0 && kk % kFlushKeys == 0) flush_main();
+        }
+      }
+      drain_gn(gam, true);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+      if (!chain) {
+        store_out(m0);
+        continue;
+      }
+      // ---- ctr2: h = f is the A operand; K-chunk kc = columns [32 kc, 32 kc + 32) lives in the warps with h == kc>>1
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        stage_begin();
+        if ((kc >> 1) == h) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float4 x[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int o = (kc & 1) * 32 + g * 16 + 4 * c;
+              x[c] = make_float4(f[o], f[o + 1], f[o + 2], f[o + 3]);
+            }
+            put16(x, g * 16);
+          }
+        }
+        stage_end();
+      }
+      // residual (this thread's own row, columns [64h, 64h+64)): first half in flight during the ctr2 MMAs
+      const int64_t m = m0 + r;
+      const bool live = m < M;
+      const float4* resp = reinterpret_cast<const float4*>(X + (live ? m : 0) * LGCN_C + h * 64);
+      float4 r4[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      drain_gn(gam + 1024, false);
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          f[cb * 32 + 4 * c] = fmaxf(f[cb * 32 + 4 * c] + r4[c].x, 0.f);
+          f[cb * 32 + 4 * c + 1] = fmaxf(f[cb * 32 + 4 * c + 1] + r4[c].y, 0.f);
+          f[cb * 32 + 4 * c + 2] = fmaxf(f[cb * 32 + 4 * c + 2] + r4[c].z, 0.f);
+          f[cb * 32 + 4 * c + 3] = fmaxf(f[cb * 32 + 4 * c + 3] + r4[c].w, 0.f);
+        }
+        if (cb == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      store_out(m0);
+    }
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------ plan: one source row per (row, key)
+struct PlanHdr {
+  int32_t n_multi, n_mcol, pad[62];
+};
+
+__global__ void k_plan_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_keys,
+                             int64_t n_nodes, int64_t n_rows_padded, int32_t* __restrict__ hdr,
+                             int32_t* __restrict__ tab, int2* __restrict__ mdesc, int32_t* __restrict__ mcol,
+                             int64_t max_multi) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_rows_padded) return;
+  int32_t* my = tab + ((m >> 7) * n_keys << 7) + (m & 127);
+  const int nb = n_keys + 1;
+  int32_t e = 0, end = 0;
+  if (m < n_nodes) {
+    e = rowptr[m];
+    end = rowptr[m + 1];
+  }
+  for (int k = 0; k < n_keys; ++k) {   // entries of a row are sorted by key (col = v * nb + k + 1)
+    int32_t val = -1;
+    const int32_t e0 = e;
+    while (e < end && col[e] % nb == k + 1) ++e;
+    const int32_t cnt = e - e0;
+    if (cnt == 1) {
+      val = col[e0] / nb;
+    } else if (cnt > 1) {
+      const int32_t i = atomicAdd(hdr, 1);
+      if (i < max_multi) {
+        const int32_t s = atomicAdd(hdr + 1, cnt);
+        mdesc[i] = make_int2(s, cnt);
+        for (int32_t j = 0; j < cnt; ++j) mcol[s + j] = col[e0 + j] / nb;
+        val = -2 - i;
+      }
+    }
+    my[(int64_t)k << 7] = val;
+  }
+}
+
+// XA[i] = sum of the source rows of multi-source entry i, in CSR (= edge-list) order; one warp per entry
+__global__ void __launch_bounds__(256)
+k_multi_sum(const float* __restrict__ X, const int32_t* __restrict__ hdr, const int2* __restrict__ mdesc,
+            const int32_t* __restrict__ mcol, float* __restrict__ XA, int64_t max_multi) {
+  const int lane = threadIdx.x & 31;
+  int64_t n = hdr[0];
+  if (n > max_multi) n = max_multi;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
+    const int2 d = mdesc[i];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t j0 = 0; j0 < d.y; j0 += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < d.y) v[u] = __ldg(reinterpret_cast<const float4*>(X + (int64_t)mcol[d.x + j0 + u] * LGCN_C) + lane);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < d.y) {
+          acc.x += v[u].x;
+          acc.y += v[u].y;
+          acc.z += v[u].z;
+          acc.w += v[u].w;
+        }
+    }
+    reinterpret_cast<float4*>(XA + i * LGCN_C)[lane] = acc;
+  }
+}
+
+bool g_attr_set = false;
+
+struct PlanView {
+  int32_t* hdr;
+  int32_t* tab;
+  int2* mdesc;
+  int32_t* mcol;
+  int64_t max_multi;
+};
+PlanView plan_view(void* plan, int64_t n_nodes, int64_t n_edges, int n_keys) {
+  PlanView v;
+  const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
+  char* p = (char*)plan;
+  v.hdr = (int32_t*)p;
+  p += 256;
+  v.tab = (int32_t*)p;
+  p += lgcn_align_up(n_tiles * n_keys * 128 * 4, 256);
+  v.max_multi = n_edges / 2;
+  v.mdesc = (int2*)p;
+  p += lgcn_align_up((v.max_multi + 1) * 8, 256);
+  v.mcol = (int32_t*)p;
+  return v;
+}
+
+}  // namespace
+
+extern "C" int64_t lgcn_laneconv_plan_bytes(int64_t n_nodes, int64_t n_edges, int n_keys) {
+  const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
+  return 256 + lgcn_align_up(n_tiles * n_keys * 128 * 4, 256) + lgcn_align_up((n_edges / 2 + 1) * 8, 256) +
+         lgcn_align_up(n_edges * 4, 256) + 256;
+}
+
+extern "C" int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes,
+                                        int64_t n_edges, void* plan, void* stream) {
+  LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "plan_build: n_keys %d", n_keys);
+  LGCN_CHECK_ARG(plan && (n_nodes == 0 || rowptr), "plan_build: NULL argument");
+  LGCN_CHECK_ARG(n_nodes >= 0 && n_edges >= 0 && n_nodes < (1ll << 31) / 16, "plan_build: sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
+  LGCN_CUDA_OK(cudaMemsetAsync(v.hdr, 0, 256, st));
+  const int64_t rows = (n_nodes + kTileM - 1) / kTileM * kTileM;
+  if (rows == 0 || n_keys == 0) return 0;
+  k_plan_build<<<lgcn_cdiv(rows, 256), 256, 0, st>>>(rowptr, col, n_keys, n_nodes, rows, v.hdr, v.tab, v.mdesc, v.mcol,
+                                                    v.max_multi);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+int64_t lgcn_laneconv_fused_aux_bytes(int64_t n_edges) { return lgcn_align_up((n_edges / 2 + 1) * LGCN_C * 4, 1024); }
+
+// out[m] = one LaneConv block of x (chain = 1) or relu(GN(sum_k W_k agg_k)) (chain = 0).  w_hi / w_lo: pre-split
+// [(n_keys + 1 (+1 with chain: ctr2)) * 128, 128]; gn: gamma1 | beta1 | gamma2 | beta2; xa: aux rows workspace.
+int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, int64_t n_edges, int n_keys,
+                               const float* w_hi, const float* w_lo, const float* gn, float* xa, int chain,
+                               cudaStream_t st) {
+  if (n_nodes <= 0) return 0;
+  LGCN_CHECK_ARG(x != out, "laneconv_fused: in-place is not possible (neighbour rows are read by other tiles)");
+  if (!g_attr_set) {
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    g_attr_set = true;
+  }
+  PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
+  if (n_keys > 0 && n_edges > 1) {
+    k_multi_sum<<<num_sms() * 4, 256, 0, st>>>(x, v.hdr, v.mdesc, v.mcol, xa, v.max_multi);
+    LGCN_LAUNCH_OK();
+  }
+  const int nkw = n_keys + 1 + (chain ? 1 : 0);
+  CUtensorMap map, mhi, mlo;
+  if (int rc = make_out_map(&map, out, LGCN_C, n_nodes, LGCN_C)) return rc;
+  if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
+  if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
+  FusedArgs a;
+  a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.n_keys = n_keys; a.chain = chain;
+  const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
+  const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
+  k_laneconv_fused<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  LGCN_LAUNCH_OK();
+  return 0;
+}

@@ -35,6 +35,9 @@ config = dict(
 
 C_ = 128
 KEEP_PAIR_QUIRK = True  # reproduce the reference's empty-scene offset behaviour
+# LaneConv blocks: True = aggregate-first single kernel (laneconv_fused.cu), False = wide projection + CSR gather +
+# ctr2 (gemm_tc_wide.cu, laneconv.cu).  LGCN_LANECONV=split selects the latter.
+LANECONV_FUSED = os.environ.get("LGCN_LANECONV", "fused") != "split"
 
 
 # --------------------------------------------------------------------------- small host-side helpers
@@ -134,6 +137,19 @@ class PackedGraph:
         self.meta = None     # f32 [N,4]   (turn0, turn1, control, intersect)
         self.ctrs = None     # SceneList over f32 [N,2]
         self.feats = None    # f32 [N,2]
+        self.n_edges = 0     # upper bound of the CSR entry count (out-of-range edges are dropped)
+        self._plan = None
+
+    def plan(self) -> Tensor:
+        """Gather plan of the aggregate-first LaneConv kernel (static per graph; shared by MapNet and M2M)."""
+        if self._plan is None:
+            lib = _C.lib()
+            self._plan = torch.empty(lib.lgcn_laneconv_plan_bytes(self.n_nodes, self.n_edges, self.n_keys),
+                                     dtype=torch.uint8, device=self.rowptr.device)
+            _C.check(lib.lgcn_laneconv_plan_build(self.rowptr.data_ptr(), self.col.data_ptr(), self.n_keys,
+                                                  self.n_nodes, self.n_edges, self._plan.data_ptr(), _C.stream_ptr()),
+                     "laneconv_plan_build")
+        return self._plan
 
     def check(self):
         """Synchronising validity check of the edge indices (tests / debugging)."""
@@ -154,7 +170,7 @@ def build_csr(edge_sets: List[Dict[str, Tensor]], n_nodes: int, device) -> Packe
     lens = [int(u.numel()) for u in us]
     E = sum(lens)
     pg = PackedGraph()
-    pg.n_nodes, pg.n_keys = n_nodes, K
+    pg.n_nodes, pg.n_keys, pg.n_edges = n_nodes, K, E
     pg.rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=device)
     pg.col = torch.empty(max(E, 1), dtype=torch.int32, device=device)
     pg.err = torch.empty(1, dtype=torch.int32, device=device)
@@ -560,6 +576,12 @@ class _LaneConvStack(nn.Module):
         if pg.n_keys != K:
             raise RuntimeError(f"lanegcn_b200: graph has {pg.n_keys} edge sets, model expects {K}")
         n = feat.shape[0]
+        if LANECONV_FUSED and lib.lgcn_get_gemm_engine() == 1:
+            ws = _Workspace.get(lib.lgcn_laneconv_planned_workspace_bytes(n, pg.n_edges, K), feat.device, "laneconv")
+            _C.check(lib.lgcn_laneconv_stack_planned(feat.data_ptr(), pg.plan().data_ptr(), pg.n_edges, K, 4,
+                                                     self._wpack().data_ptr(), n, ws.data_ptr(), _C.stream_ptr()),
+                     "laneconv_stack_planned")
+            return feat
         ws = _Workspace.get(lib.lgcn_laneconv_workspace_bytes(n, K), feat.device, "laneconv")
         _C.check(lib.lgcn_laneconv_stack(feat.data_ptr(), pg.rowptr.data_ptr(), pg.col.data_ptr(), K, 4,
                                          self._wpack().data_ptr(), n, ws.data_ptr(), _C.stream_ptr()),

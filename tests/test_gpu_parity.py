@@ -29,13 +29,19 @@ def net(cuda, lib):
     return n.to(cuda).eval()
 
 
-@pytest.fixture(params=[0, 1], ids=["simt", "tcgen05"])
+@pytest.fixture(params=[0, 1, 2], ids=["simt", "tcgen05", "tcgen05-split"])
 def engine(request, lib):
-    prev = lib.lgcn_set_gemm_engine(request.param)
-    if lib.lgcn_get_gemm_engine() != request.param:
+    """0: fp32 SIMT validation engine; 1: tcgen05 with the aggregate-first LaneConv kernel (the default);
+    2: tcgen05 with the wide projection + CSR gather + ctr2 LaneConv path."""
+    eng = min(request.param, 1)
+    prev = lib.lgcn_set_gemm_engine(eng)
+    if lib.lgcn_get_gemm_engine() != eng:
         lib.lgcn_set_gemm_engine(prev)
         pytest.skip("engine not built")
-    yield request.param
+    prev_fused = L.LANECONV_FUSED
+    L.LANECONV_FUSED = request.param == 1
+    yield eng
+    L.LANECONV_FUSED = prev_fused
     lib.lgcn_set_gemm_engine(prev)
 
 
@@ -272,6 +278,51 @@ def test_gather_gn_relu_matches_index_add_order(cuda, lib):
     _C.check(lib.lgcn_laneconv_gather_gn_relu(dY.data_ptr(), K + 1, pg.rowptr.data_ptr(), pg.col.data_ptr(),
                                               dg.data_ptr(), db.data_ptr(), out2.data_ptr(), n, sp()))
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("n,n_keys,n_blocks,seed", [(1, 14, 1, 0), (127, 14, 2, 1), (129, 3, 3, 2), (1000, 14, 4, 3),
+                                                     (4097, 14, 4, 4), (300, 0, 2, 5), (20000, 14, 1, 6)])
+def test_laneconv_stack_planned_matches_split_fp32(cuda, lib, n, n_keys, n_blocks, seed):
+    """Aggregate-first single-kernel LaneConv stack (tcgen05) vs the projection + gather + ctr2 stack on the fp32
+    SIMT engine: random graphs with empty keys, multi-source (row, key) pairs, a hub row and row tails."""
+    g = torch.Generator().manual_seed(100 + seed)
+    sets = []
+    for k in range(n_keys):
+        e = 0 if k == 2 else int(n * (0.9 if k % 3 else 1.5)) + (k == 0)
+        u, v = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+        if k == 1 and n > 64:
+            u[: min(e, 300)] = 5   # hub: one destination with hundreds of sources of one key
+        sets.append({"u": u.to(cuda), "v": v.to(cuda)})
+    pg = L.build_csr(sets, n, cuda)
+    nb = n_keys + 1
+    per = lib.lgcn_laneconv_wpack_floats(n_keys)
+    wp = torch.empty(n_blocks * per)
+    for i in range(n_blocks):
+        o = i * per
+        wp[o:o + (nb + 1) * 128 * 128] = torch.randn((nb + 1) * 128 * 128, generator=g) * (0.7 / (128 ** 0.5))
+        wp[o + (nb + 1) * 128 * 128:o + per] = torch.randn(4 * 128, generator=g) * 0.3 + torch.tensor([1.0, 0.0, 1.0, 0.0]).repeat_interleave(128)
+    wp = wp.to(cuda)
+    x = torch.randn(n, 128, generator=g).to(cuda)
+
+    prev = lib.lgcn_set_gemm_engine(0)
+    try:
+        want = x.clone()
+        ws = torch.empty(lib.lgcn_laneconv_workspace_bytes(n, n_keys), dtype=torch.uint8, device=cuda)
+        _C.check(lib.lgcn_laneconv_stack(want.data_ptr(), pg.rowptr.data_ptr(), pg.col.data_ptr(), n_keys, n_blocks,
+                                         wp.data_ptr(), n, ws.data_ptr(), sp()))
+        if lib.lgcn_set_gemm_engine(1) != 0 or lib.lgcn_get_gemm_engine() != 1:
+            pytest.skip("tcgen05 engine not built")
+        got = x.clone()
+        ws2 = torch.empty(lib.lgcn_laneconv_planned_workspace_bytes(n, pg.n_edges, n_keys), dtype=torch.uint8, device=cuda)
+        _C.check(lib.lgcn_laneconv_stack_planned(got.data_ptr(), pg.plan().data_ptr(), pg.n_edges, n_keys, n_blocks,
+                                                 wp.data_ptr(), n, ws2.data_ptr(), sp()))
+        assert_close(got, want, "planned LaneConv stack", rtol=RTOL, atol=ATOL)
+        again = x.clone()
+        _C.check(lib.lgcn_laneconv_stack_planned(again.data_ptr(), pg.plan().data_ptr(), pg.n_edges, n_keys, n_blocks,
+                                                 wp.data_ptr(), n, ws2.data_ptr(), sp()))
+        assert torch.equal(got, again), "planned LaneConv stack is not deterministic"
+    finally:
+        lib.lgcn_set_gemm_engine(prev)
 
 
 def test_segsum_gn_relu(cuda, lib):
