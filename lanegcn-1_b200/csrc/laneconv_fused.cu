@@ -40,7 +40,8 @@ constexpr int kAStages = 4;
 constexpr int kSmemOut = kWStages * kWStageBytes;            // 160 KB: 8 x 4 KB store staging
 constexpr int kSmemGam = kSmemOut + 8 * 4096;                // gamma1 | beta1 | gamma2 | beta2 (4 x 512 B)
 constexpr int kSmemStat = kSmemGam + 4 * 512;                // float2 [2][128]
-constexpr int kSmemBar = kSmemStat + 2 * 128 * 8;
+constexpr int kSmemTab = kSmemStat + 2 * 128 * 8;            // int32 [4][256]: table entries in flight (cp.async)
+constexpr int kSmemBar = kSmemTab + 4 * 256 * 4;
 constexpr int kSmemTotal = kSmemBar + 256;
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 1;
@@ -52,6 +53,11 @@ constexpr uint32_t kColMain = 256, kColCross = 384;
 // holds values 2^-11 smaller and runs through.
 constexpr int kFlushKeys = 3;
 
+// cvt.rna.tf32.f32 for finite inputs (round to nearest, ties away from zero, on the sign-magnitude bit pattern):
+// two integer instructions instead of the multi-instruction sequence ptxas emits for the cvt (which also handles
+// Inf / NaN; features never are)
+__device__ __forceinline__ float rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 struct FusedArgs {
   const float* X;        // [M,128] input features (also the residual)
   const float* XA;       // auxiliary rows (multi-source sums)
@@ -60,6 +66,7 @@ struct FusedArgs {
   int64_t M;
   int n_keys;
   int chain;             // 1: ctr2 + GN + residual + ReLU inside the kernel
+  int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes)
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -111,6 +118,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const int32_t* __restrict__ tab = a.tab;
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
   const bool chain = a.chain != 0;
+  const int dbg = a.dbg;
+  const int flush_keys = (dbg & 64) ? (1 << 20) : kFlushKeys;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
   const int64_t grid = gridDim.x;
   const int keys_per_tile = nk + (chain ? 1 : 0);   // key nk = ctr2 (weights follow the projections in w_hi / w_lo)
@@ -150,12 +159,12 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
       for (int kk = 0; kk < keys_per_tile; ++kk) {
         const bool fresh_all = kk == 0 || kk == nk;                         // projections / ctr2 start
-        const bool fresh_main = fresh_all || (kk < nk && kk % kFlushKeys == 0);   // main restarts after a flush
+        const bool fresh_main = fresh_all || (kk < nk && kk % flush_keys == 0);   // main restarts after a flush
         if (fresh_main) {
           mbar_wait(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have read the accumulator(s)
           ++acc_uses;
         }
-        const bool publish = kk >= nk - 1 || (kk + 1) % kFlushKeys == 0;     // a flush / drain follows this key
+        const bool publish = kk >= nk - 1 || (kk + 1) % flush_keys == 0;     // a flush / drain follows this key
         for (int kc = 0; kc < 4; ++kc) {
           mbar_wait(bar_w_full + 8 * ws, w_phase);
           mbar_wait(bar_a_full + 8 * as, a_phase);
@@ -166,6 +175,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
             const uint32_t w_hi = sbase + ws * kWStageBytes, w_lo = w_hi + kWStageBytes / 2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+              if (dbg & 4) break;
               const bool k0 = kc == 0 && j == 0;
               umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_all && k0) ? 0u : 1u);
               umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
@@ -196,56 +206,64 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     const uint32_t stat_mine = sbase + kSmemStat + (h * 128 + r) * 8, stat_other = sbase + kSmemStat + ((h ^ 1) * 128 + r) * 8;
     const uint32_t gam = sbase + kSmemGam + h * 256;   // + 0: gamma1, + 512: beta1, + 1024: gamma2, + 1536: beta2
 
-    // ---- prefetch cursor: two stages ahead of the stage being converted
-    int64_t pt = blockIdx.x;
-    int pkk = 0, pkc = 0;
-    auto self_v = [&](int64_t t) -> int {
-      const int64_t m = t * kTileM + r;
-      return (t < n_tiles && m < M) ? (int)m : -1;
-    };
-    auto tab_v = [&](int64_t t, int kk) -> int {
-      return t < n_tiles ? __ldg(tab + ((t * n_keys + (kk - 1)) << 7) + r) : -1;
-    };
-    int pv = self_v(pt);
-    int pv_next = nk > 1 ? tab_v(pt, 1) : self_v(pt + grid);
-    float4 xq[2][4];
-    auto fetch = [&](float4(&dst)[4]) {
-      const float* p = pv >= 0 ? X + (int64_t)pv * LGCN_C : XA + (int64_t)(pv < -1 ? -2 - pv : 0) * LGCN_C;
-      const float4* s = reinterpret_cast<const float4*>(p + pkc * 32 + h * 16);
-      const bool live = pv != -1;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dst[c] = live ? __ldg(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (++pkc == 4) {   // next key: its table entry was requested four stages ago
-        pkc = 0;
-        pv = pv_next;
-        if (++pkk == nk) {
-          pkk = 0;
-          pt += grid;
-        }
-        int nkk = pkk + 1;
-        int64_t nt = pt;
-        if (nkk == nk) {
-          nkk = 0;
-          nt = pt + grid;
-        }
-        pv_next = nkk == 0 ? self_v(nt) : tab_v(nt, nkk);
+    // ---- sources.  The table entry of (row r, key kk) is needed two keys after it is requested; it travels through
+    // shared memory with cp.async so that no register (and no scoreboard wait on a spill of it) is involved.
+    const int n_tiles_i = (int)n_tiles, grid_i = (int)grid;
+    const uint32_t slot0 = sbase + kSmemTab + (e * 32 + lane) * 4;   // + 1024 * (key parity ring index)
+    auto key_norm = [&](int& t, int& kk) {
+      while (kk >= nk) {
+        kk -= nk;
+        t += grid_i;
       }
+    };
+    auto self_src = [&](int t) -> int {
+      const int64_t m = (int64_t)t * kTileM + r;
+      return (t < n_tiles_i && m < M) ? (int)m : -1;
+    };
+    auto request = [&](int t, int kk, int ring) {   // one cp.async group per call (possibly empty)
+      key_norm(t, kk);
+      if (kk > 0 && t < n_tiles_i) {
+        const int32_t* src = tab + (((int64_t)t * n_keys + (kk - 1)) << 7) + r;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(slot0 + 1024u * ring), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto receive = [&](int t, int kk, int ring) -> int {   // all but the newest request have landed
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      key_norm(t, kk);
+      if (t >= n_tiles_i) return -1;
+      if (kk == 0) return self_src(t);
+      int v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot0 + 1024u * ring) : "memory");
+      return v;
+    };
+    float4 xq[2][4];   // the chunks of the next two stages (loads in flight)
+    auto fetch = [&](float4(&dst)[4], int v, int kc) {
+      const float* p = v >= 0 ? X + (int64_t)v * LGCN_C : XA + (int64_t)(v < -1 ? -2 - v : 0) * LGCN_C;
+      const float4* s = reinterpret_cast<const float4*>(p + kc * 32 + h * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = (v != -1 && !(dbg & 8)) ? __ldg(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     uint32_t a_phase = 0, acc_uses = 0;
     int as = 0;
-    // 16 floats -> hi/lo -> TMEM columns [c0, c0+16) (hi) and [c0+32, c0+48) (lo) of A stage `as`
+    // 16 floats -> hi/lo -> TMEM columns [c0, c0+16) (hi) and [c0+32, c0+48) (lo) of A stage `as`; eight columns per
+    // tcgen05.st keeps the live temporaries at 16 registers
     auto put16 = [&](const float4(&x)[4], int c0) {
-      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float h0 = tf32_rna(x[c].x), h1 = tf32_rna(x[c].y), h2 = tf32_rna(x[c].z), h3 = tf32_rna(x[c].w);
-        hi[4 * c] = __float_as_uint(h0); lo[4 * c] = __float_as_uint(tf32_rna(x[c].x - h0));
-        hi[4 * c + 1] = __float_as_uint(h1); lo[4 * c + 1] = __float_as_uint(tf32_rna(x[c].y - h1));
-        hi[4 * c + 2] = __float_as_uint(h2); lo[4 * c + 2] = __float_as_uint(tf32_rna(x[c].z - h2));
-        hi[4 * c + 3] = __float_as_uint(h3); lo[4 * c + 3] = __float_as_uint(tf32_rna(x[c].w - h3));
+      for (int g = 0; g < 2; ++g) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 y = x[2 * g + c];
+          const float h0 = rna(y.x), h1 = rna(y.y), h2 = rna(y.z), h3 = rna(y.w);
+          hi[4 * c] = __float_as_uint(h0); lo[4 * c] = __float_as_uint(rna(y.x - h0));
+          hi[4 * c + 1] = __float_as_uint(h1); lo[4 * c + 1] = __float_as_uint(rna(y.y - h1));
+          hi[4 * c + 2] = __float_as_uint(h2); lo[4 * c + 2] = __float_as_uint(rna(y.z - h2));
+          hi[4 * c + 3] = __float_as_uint(h3); lo[4 * c + 3] = __float_as_uint(rna(y.w - h3));
+        }
+        TMEM_ST8(t_lane + as * 64 + c0 + 8 * g, hi, 0);
+        TMEM_ST8(t_lane + as * 64 + 32 + c0 + 8 * g, lo, 0);
       }
-      TMEM_ST16(t_lane + as * 64 + c0, hi, 0);
-      TMEM_ST16(t_lane + as * 64 + 32 + c0, lo, 0);
     };
     auto stage_begin = [&]() {
       mbar_wait(bar_a_empty + 8 * as, a_phase ^ 1);
@@ -330,6 +348,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     auto store_out = [&](int64_t m0) {   // f -> two 32 x 32 boxes through the 4 KB staging buffer
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
+        if (dbg & 1) break;
         if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
 #pragma unroll
@@ -348,23 +367,32 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
     };
 
-    fetch(xq[0]);
-    fetch(xq[1]);
+    int ring = 0;   // key counter & 3
+    request((int)blockIdx.x, 1, 1);
+    request((int)blockIdx.x, 2, 2);
+    int v_cur = self_src((int)blockIdx.x), v_next = receive((int)blockIdx.x, 1, 1);
+    fetch(xq[0], v_cur, 0);
+    fetch(xq[1], v_cur, 1);
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
       const int64_t m0 = t * kTileM;
 #pragma unroll
       for (int c = 0; c < 64; ++c) f[c] = 0.f;
       for (int kk = 0; kk < nk; ++kk) {
+        // entry of key kk+3 requested now, entry of key kk+2 (requested one key ago) received after this key
+        request((int)t, kk + 3, (ring + 3) & 3);
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
           stage_begin();
-          put16(xq[kc & 1], h * 16);
-          fetch(xq[kc & 1]);   // stage + 2
+          if (!(dbg & 32)) put16(xq[kc & 1], h * 16);
+          fetch(xq[kc & 1], kc < 2 ? v_cur : v_next, (kc + 2) & 3);   // stage + 2
           stage_end();
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
           // warp resumes
-          if (kc == 2 && kk > 0 && kk % kFlushKeys == 0) flush_main();
+          if (kc == 2 && kk > 0 && kk % flush_keys == 0) flush_main();
         }
+        v_cur = v_next;
+        v_next = receive((int)t, kk + 2, (ring + 2) & 3);
+        ring = (ring + 1) & 3;
       }
       drain_gn(gam, true);
 #pragma unroll
@@ -564,7 +592,7 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
   if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
   FusedArgs a;
-  a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.n_keys = n_keys; a.chain = chain;
+  a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.n_keys = n_keys; a.chain = chain; a.dbg = lgcn_debug_get();
   const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
   k_laneconv_fused<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);

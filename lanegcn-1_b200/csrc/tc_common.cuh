@@ -117,6 +117,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         "r"(v[base + 15]), "r"(taddr)                                                                         \
       : "memory")
 
+#define TMEM_ST8(taddr, v, base)                                                                              \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"                       \
+               ::"r"(v[base + 0]), "r"(v[base + 1]), "r"(v[base + 2]), "r"(v[base + 3]), "r"(v[base + 4]),    \
+                 "r"(v[base + 5]), "r"(v[base + 6]), "r"(v[base + 7]), "r"(taddr)                             \
+               : "memory")
+
 #define TMEM_LD16(v, base, taddr)                                                                             \
   asm volatile(                                                                                               \
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"  \
