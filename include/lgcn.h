@@ -44,6 +44,9 @@ int lgcn_set_gemm_engine(int engine);
  * 4 = MMA issuer skips the tcgen05.mma instructions, 8 = producers skip global loads and conversion,
  * 16 = route the multi-block projection through the generic kernel instead of the A-in-TMEM one (results stay right). */
 int lgcn_debug_flags(int flags);
+/* Profiling aid: device buffer [1024][8] of int64 clock stamps filled by CTA 0 of the aggregate-first LaneConv kernel
+ * while debug flag 256 is set (tools/timeline_fused.py). */
+int lgcn_debug_timeline(long long* device_buffer);
 /* number of CUDA kernels this library has launched in this process (all entry points) */
 int64_t lgcn_launch_count(void);
 /* Per-kernel timing for the benchmark: while enabled, lgcn_laneconv_stack / lgcn_att_forward bracket their

@@ -51,6 +51,7 @@ _SIGS = {
     "lgcn_laneconv_wpack_floats": (_i64, [_i32]),
     "lgcn_laneconv_workspace_bytes": (_i64, [_i64, _i32]),
     "lgcn_laneconv_stack": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "lgcn_debug_timeline": (_i32, [_vp]),
     "lgcn_laneconv_plan_bytes": (_i64, [_i64, _i64, _i32]),
     "lgcn_laneconv_plan_build": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp]),
     "lgcn_laneconv_planned_workspace_bytes": (_i64, [_i64, _i64, _i32]),

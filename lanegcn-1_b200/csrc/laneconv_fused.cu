@@ -34,10 +34,12 @@ using namespace tc;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kWStages = 5;
+constexpr int kWStages = 4;
+constexpr int kXStages = 3;                                  // raw fp32 A chunks in flight (cp.async ring)
 constexpr int kWStageBytes = 2 * 128 * 128;                  // hi 16 KB | lo 16 KB
 constexpr int kAStages = 4;
-constexpr int kSmemOut = kWStages * kWStageBytes;            // 160 KB: 8 x 4 KB store staging
+constexpr int kSmemX = kWStages * kWStageBytes;              // 128 KB: X ring, kXStages x (8 warps x 32 rows x 64 B)
+constexpr int kSmemOut = kSmemX + kXStages * 16384;          // 8 x 4 KB store staging
 constexpr int kSmemGam = kSmemOut + 8 * 4096;                // gamma1 | beta1 | gamma2 | beta2 (4 x 512 B)
 constexpr int kSmemStat = kSmemGam + 4 * 512;                // float2 [2][128]
 constexpr int kSmemTab = kSmemStat + 2 * 128 * 8;            // int32 [4][256]: table entries in flight (cp.async)
@@ -66,7 +68,8 @@ struct FusedArgs {
   int64_t M;
   int n_keys;
   int chain;             // 1: ctr2 + GN + residual + ReLU inside the kernel
-  int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes)
+  long long* tl;         // timeline buffer [1024][8] (dbg & 256, CTA 0 only)
+  int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes, 128 no weight loads)
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -77,22 +80,20 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   if (sbase & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t bar_w_full = sbase + kSmemBar;             // [5]
-  const uint32_t bar_w_empty = bar_w_full + 8 * kWStages;   // [5]
-  const uint32_t bar_a_full = bar_w_empty + 8 * kWStages;   // [4]
-  const uint32_t bar_a_empty = bar_a_full + 8 * kAStages;   // [4]
-  const uint32_t bar_acc_full = bar_a_empty + 8 * kAStages;
+  // One full / empty barrier pair per stage serves both rings (weights in shared memory, A in tensor memory): the MMA
+  // warp pays one try_wait and one tcgen05.commit per stage instead of two (each costs the issuing thread ~200 cycles
+  // during which the tensor pipe, whose queue is only a couple of instructions deep, runs dry).
+  static_assert(kWStages == kAStages, "the weight ring and the A ring share their barriers");
+  const uint32_t bar_full = sbase + kSmemBar;               // [4]: 8 producer-warp arrives + the TMA expect_tx arrive
+  const uint32_t bar_empty = bar_full + 8 * kAStages;       // [4]: tcgen05.commit
+  const uint32_t bar_acc_full = bar_empty + 8 * kAStages;
   const uint32_t bar_acc_empty = bar_acc_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + 192);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWStages; ++i) {
-      mbar_init(bar_w_full + 8 * i, 1);
-      mbar_init(bar_w_empty + 8 * i, 1);
-    }
     for (int i = 0; i < kAStages; ++i) {
-      mbar_init(bar_a_full + 8 * i, 8);   // one arrive per producer warp
-      mbar_init(bar_a_empty + 8 * i, 1);
+      mbar_init(bar_full + 8 * i, 9);
+      mbar_init(bar_empty + 8 * i, 1);
     }
     mbar_init(bar_acc_full, 1);
     mbar_init(bar_acc_empty, 8);
@@ -119,6 +120,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
   const bool chain = a.chain != 0;
   const int dbg = a.dbg;
+  long long* tl = (blockIdx.x == 0 && (dbg & 256)) ? a.tl : nullptr;
   const int flush_keys = (dbg & 64) ? (1 << 20) : kFlushKeys;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
   const int64_t grid = gridDim.x;
@@ -131,10 +133,13 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
       for (int kk = 0; kk < keys_per_tile; ++kk) {
         for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(bar_w_empty + 8 * ws, phase ^ 1);
+          mbar_wait(bar_empty + 8 * ws, phase ^ 1);
           if (elect_one()) {
-            const uint32_t bar = bar_w_full + 8 * ws, dst = sbase + ws * kWStageBytes;
+            const uint32_t bar = bar_full + 8 * ws, dst = sbase + ws * kWStageBytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWStageBytes) : "memory");
+            if (dbg & 128) {   // ablation: no weight loads
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"((uint32_t)kWStageBytes) : "memory");
+            } else {
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&whi_map)), "r"(bar), "r"(kc * 32), "r"(kk * 128)
@@ -143,6 +148,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                 ::"r"(dst + kWStageBytes / 2), "l"(reinterpret_cast<uint64_t>(&wlo_map)), "r"(bar), "r"(kc * 32), "r"(kk * 128)
                 : "memory");
+            }
           }
           __syncwarp();
           if (++ws == kWStages) {
@@ -154,25 +160,48 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     }
   } else if (warp == kMmaWarp) {
     // =========================================================== MMA issuer
-    uint32_t w_phase = 0, a_phase = 0, acc_uses = 0;
-    int ws = 0, as = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
-      for (int kk = 0; kk < keys_per_tile; ++kk) {
-        const bool fresh_all = kk == 0 || kk == nk;                         // projections / ctr2 start
-        const bool fresh_main = fresh_all || (kk < nk && kk % flush_keys == 0);   // main restarts after a flush
-        if (fresh_main) {
-          mbar_wait(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have read the accumulator(s)
-          ++acc_uses;
-        }
-        const bool publish = kk >= nk - 1 || (kk + 1) % flush_keys == 0;     // a flush / drain follows this key
-        for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(bar_w_full + 8 * ws, w_phase);
-          mbar_wait(bar_a_full + 8 * as, a_phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t d_main = tmem_base + kColMain, d_cross = tmem_base + kColCross;
-            const uint32_t a_hi = tmem_base + as * 64, a_lo = a_hi + 32;
-            const uint32_t w_hi = sbase + ws * kWStageBytes, w_lo = w_hi + kWStageBytes / 2;
+    // The full barrier of stage s+1 is TESTED (non-blocking) before the MMAs of stage s are issued and the predicate is
+    // read after them, so the ~200-cycle round trip of the test overlaps the issue; the blocking wait runs only when
+    // the producers are not ahead (tools/timeline_fused.py).
+    // ONE elected thread runs the whole loop (waits included): no per-stage elect / __syncwarp.
+    if (elect_one()) {
+      uint32_t phase = 0, acc_uses = 0;
+      int st = 0, tls = 0;
+      const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + grid - 1) / grid : 0;
+      int64_t stages_left = my_tiles * keys_per_tile * 4;
+      asm volatile(".reg .pred lgcn_peek;");
+      if (stages_left > 0) {
+        mbar_wait(bar_full, 0);
+        tc_fence_after();
+      }
+      const uint32_t d_main = tmem_base + kColMain, d_cross = tmem_base + kColCross;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
+        int since = 0;   // keys accumulated in main since its last restart
+        for (int kk = 0; kk < keys_per_tile; ++kk) {
+          const bool fresh_all = kk == 0 || kk == nk;                     // projections / ctr2 start
+          const bool fresh_main = fresh_all || since == flush_keys;       // main restarts after a flush
+          if (fresh_main) {
+            since = 0;
+            mbar_wait(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have read the accumulator(s)
+            ++acc_uses;
+            tc_fence_after();
+          }
+          ++since;
+          const bool publish = kk >= nk - 1 || since == flush_keys;       // a flush / drain follows this key
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            const uint32_t a_hi = tmem_base + st * 64, a_lo = a_hi + 32;
+            const uint32_t w_hi = sbase + st * kWStageBytes, w_lo = w_hi + kWStageBytes / 2;
+            int st2 = st + 1;
+            uint32_t ph2 = phase;
+            if (st2 == kAStages) {
+              st2 = 0;
+              ph2 ^= 1;
+            }
+            --stages_left;
+            if (tl && tls < 1024) tl[tls * 8 + 0] = clock64();
+            asm volatile("mbarrier.test_wait.parity.shared::cta.b64 lgcn_peek, [%0], %1;" ::"r"(bar_full + 8 * st2), "r"(ph2)
+                         : "memory");
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (dbg & 4) break;
@@ -181,22 +210,24 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
               umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
               umma_tf32_ts(d_main, a_hi + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_main && k0) ? 0u : 1u);
             }
-            umma_commit(bar_w_empty + 8 * ws);
-            umma_commit(bar_a_empty + 8 * as);
+            umma_commit(bar_empty + 8 * st);
             if (publish && kc == 3) umma_commit(bar_acc_full);
-          }
-          __syncwarp();
-          if (++ws == kWStages) {
-            ws = 0;
-            w_phase ^= 1;
-          }
-          if (++as == kAStages) {
-            as = 0;
-            a_phase ^= 1;
+            if (tl && tls < 1024) tl[tls * 8 + 1] = clock64();
+            uint32_t ready;
+            asm volatile("selp.u32 %0, 1, 0, lgcn_peek;" : "=r"(ready));
+            if (stages_left > 0) {
+              if (!ready) mbar_wait(bar_full + 8 * st2, ph2);
+              tc_fence_after();
+            }
+            if (tl && tls < 1024) tl[tls * 8 + 2] = clock64();
+            ++tls;
+            st = st2;
+            phase = ph2;
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // =========================================================== A producers + epilogue: warps 4..11
     const int e = warp - 4, q = e & 3, h = e >> 2;
@@ -206,10 +237,14 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     const uint32_t stat_mine = sbase + kSmemStat + (h * 128 + r) * 8, stat_other = sbase + kSmemStat + ((h ^ 1) * 128 + r) * 8;
     const uint32_t gam = sbase + kSmemGam + h * 256;   // + 0: gamma1, + 512: beta1, + 1024: gamma2, + 1536: beta2
 
-    // ---- sources.  The table entry of (row r, key kk) is needed two keys after it is requested; it travels through
-    // shared memory with cp.async so that no register (and no scoreboard wait on a spill of it) is involved.
+    // ---- A feed.  Rows are gathered with cp.async (global -> shared, no registers, three stages in flight): four
+    // lanes fetch the 64 B slice of one source row, so a warp-wide 16 B request touches 8 rows instead of 32 (with one
+    // row per lane the L1 tag stage, one lookup per distinct line, was the limiter).  The owner lane of a row then
+    // reads its 64 B back (XOR-swizzled 16 B pieces: conflict-free both ways), splits hi/lo and stores to TMEM.
+    // Table entries (source row of (r, key)) travel the same way, two keys ahead.
     const int n_tiles_i = (int)n_tiles, grid_i = (int)grid;
-    const uint32_t slot0 = sbase + kSmemTab + (e * 32 + lane) * 4;   // + 1024 * (key parity ring index)
+    const uint32_t slot0 = sbase + kSmemTab + (e * 32 + lane) * 4;   // + 1024 * (key index & 3)
+    const uint32_t xblk = sbase + kSmemX + e * 2048;                 // + 16384 * slot: this warp's 32 rows x 64 B
     auto key_norm = [&](int& t, int& kk) {
       while (kk >= nk) {
         kk -= nk;
@@ -220,29 +255,45 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       const int64_t m = (int64_t)t * kTileM + r;
       return (t < n_tiles_i && m < M) ? (int)m : -1;
     };
-    auto request = [&](int t, int kk, int ring) {   // one cp.async group per call (possibly empty)
+    auto request = [&](int t, int kk, int ring) {   // joins the cp.async group of the current stage
       key_norm(t, kk);
       if (kk > 0 && t < n_tiles_i) {
         const int32_t* src = tab + (((int64_t)t * n_keys + (kk - 1)) << 7) + r;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(slot0 + 1024u * ring), "l"(src) : "memory");
       }
+    };
+    // sources of the four rows this lane fetches for (tile t, key kk): rows 8i + (lane >> 2) of the warp's block
+    auto sources = [&](int t, int kk, int ring, int (&vr)[4]) {
+      key_norm(t, kk);
+      int v = -1;
+      if (t < n_tiles_i) {
+        if (kk == 0) v = self_src(t);
+        else asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot0 + 1024u * ring) : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vr[i] = __shfl_sync(0xffffffffu, v, 8 * i + (lane >> 2));
+    };
+    const uint32_t piece = lane & 3;
+    auto issue = [&](const int (&vr)[4], int kc, int slot) {   // 4 x 16 B per lane; one commit group per stage
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int v = vr[i];
+        const int row = 8 * i + (lane >> 2);
+        const float* p = v >= 0 ? X + (int64_t)v * LGCN_C : XA + (int64_t)(v < -1 ? -2 - v : 0) * LGCN_C;
+        const uint32_t dst = xblk + slot * 16384 + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
+        const uint32_t n = (v != -1 && !(dbg & 8)) ? 16u : 0u;   // 0 source bytes: the 16 B are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p + kc * 32 + h * 16 + piece * 4), "r"(n)
+                     : "memory");
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto receive = [&](int t, int kk, int ring) -> int {   // all but the newest request have landed
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-      key_norm(t, kk);
-      if (t >= n_tiles_i) return -1;
-      if (kk == 0) return self_src(t);
-      int v;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot0 + 1024u * ring) : "memory");
-      return v;
-    };
-    float4 xq[2][4];   // the chunks of the next two stages (loads in flight)
-    auto fetch = [&](float4(&dst)[4], int v, int kc) {
-      const float* p = v >= 0 ? X + (int64_t)v * LGCN_C : XA + (int64_t)(v < -1 ? -2 - v : 0) * LGCN_C;
-      const float4* s = reinterpret_cast<const float4*>(p + kc * 32 + h * 16);
+    auto take = [&](float4(&cur)[4], int slot) {   // this lane's row: 64 B of the slot (stage s; s+1, s+2 may be pending)
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncwarp();
+      const uint32_t src = xblk + slot * 16384 + lane * 64;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) dst[c] = (v != -1 && !(dbg & 8)) ? __ldg(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 4; ++c) cur[c] = ld_shared_f4(src + ((c ^ ((lane >> 1) & 3)) << 4));
+      __syncwarp();   // every lane has read: the slot may be refilled
     };
     uint32_t a_phase = 0, acc_uses = 0;
     int as = 0;
@@ -266,14 +317,14 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
     };
     auto stage_begin = [&]() {
-      mbar_wait(bar_a_empty + 8 * as, a_phase ^ 1);
+      mbar_wait(bar_empty + 8 * as, a_phase ^ 1);
       tc_fence_after();
     };
     auto stage_end = [&]() {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a_full + 8 * as);
+      if (lane == 0) mbar_arrive(bar_full + 8 * as);
       if (++as == kAStages) {
         as = 0;
         a_phase ^= 1;
@@ -367,32 +418,93 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
     };
 
-    int ring = 0;   // key counter & 3
+    // prologue: table entries of keys 1 and 2, chunks of stages 0..2
+    int vr[4], vrn[4];
+    int kseq = 0;   // running key count & 3: ring slot of a table entry = (kseq + distance) & 3
     request((int)blockIdx.x, 1, 1);
-    request((int)blockIdx.x, 2, 2);
-    int v_cur = self_src((int)blockIdx.x), v_next = receive((int)blockIdx.x, 1, 1);
-    fetch(xq[0], v_cur, 0);
-    fetch(xq[1], v_cur, 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    sources((int)blockIdx.x, 0, 0, vr);
+#pragma unroll
+    for (int s0 = 0; s0 < kXStages; ++s0) issue(vr, s0, s0);   // stages 0..2 = chunks 0..2 of key 0 (kXStages <= 4)
+    int xs = 0;   // ring slot of the stage being converted
+    int tls = 0;
+    // second epilogue of a tile (ctr2 accumulators -> GroupNorm + residual + ReLU -> store).  It runs three stages
+    // into the NEXT tile: those stages are produced while the ctr2 MMAs still execute, the accumulators are drained
+    // the moment ctr2 retires, and the tensor pipe then has three stages of queued work while the norm, the residual
+    // and the stores are done (a first version finished the tile first and idled the pipe ~7 k cycles per tile).
+    auto finish_tile = [&](int64_t pm0) {
+      const int64_t m = pm0 + r;
+      const bool live = m < M;
+      const float4* resp = reinterpret_cast<const float4*>(X + (live ? m : 0) * LGCN_C + h * 64);
+      float4 r4[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      drain_gn(gam + 1024, false);
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          f[cb * 32 + 4 * c] = fmaxf(f[cb * 32 + 4 * c] + r4[c].x, 0.f);
+          f[cb * 32 + 4 * c + 1] = fmaxf(f[cb * 32 + 4 * c + 1] + r4[c].y, 0.f);
+          f[cb * 32 + 4 * c + 2] = fmaxf(f[cb * 32 + 4 * c + 2] + r4[c].z, 0.f);
+          f[cb * 32 + 4 * c + 3] = fmaxf(f[cb * 32 + 4 * c + 3] + r4[c].w, 0.f);
+        }
+        if (cb == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      store_out(pm0);
+    };
+    bool pending = false;
+    int64_t pending_m0 = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
       const int64_t m0 = t * kTileM;
+      if (!pending) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) f[c] = 0.f;
+        for (int c = 0; c < 64; ++c) f[c] = 0.f;
+      }
+      int since = 0;   // keys accumulated in the main accumulator since its last restart
       for (int kk = 0; kk < nk; ++kk) {
-        // entry of key kk+3 requested now, entry of key kk+2 (requested one key ago) received after this key
-        request((int)t, kk + 3, (ring + 3) & 3);
+        const bool flush_here = kk > 0 && since == flush_keys;
+        if (flush_here) since = 0;
+        ++since;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
+          if (kc == 3 && kk == 0 && pending) {   // before stage 3 of the new tile
+            finish_tile(pending_m0);
+            pending = false;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) f[c] = 0.f;
+          }
+          float4 cur[4];
+          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 3] = clock64();
+          take(cur, xs);
+          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 4] = clock64();
+          if (kc == 0) {
+            // all groups but the two newest have landed: the entry of key kk+1 (requested a key ago) is readable
+            sources((int)t, kk + 1, (kseq + 1) & 3, vrn);
+            request((int)t, kk + 2, (kseq + 2) & 3);   // joins this stage's group
+          }
+          // refill the slot with stage + 3: chunk kc+3 of this key (kc == 0) or chunk kc-1 of the next key
+          if (kc == 0) issue(vr, 3, xs);
+          else issue(vrn, kc - 1, xs);
+          if (++xs == kXStages) xs = 0;
           stage_begin();
-          if (!(dbg & 32)) put16(xq[kc & 1], h * 16);
-          fetch(xq[kc & 1], kc < 2 ? v_cur : v_next, (kc + 2) & 3);   // stage + 2
+          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 5] = clock64();
+          if (!(dbg & 32)) put16(cur, h * 16);
           stage_end();
+          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 6] = clock64();
+          ++tls;
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
           // warp resumes
-          if (kc == 2 && kk > 0 && kk % flush_keys == 0) flush_main();
+          if (kc == 2 && flush_here) flush_main();
         }
-        v_cur = v_next;
-        v_next = receive((int)t, kk + 2, (ring + 2) & 3);
-        ring = (ring + 1) & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vr[i] = vrn[i];
+        kseq = (kseq + 1) & 3;
       }
       drain_gn(gam, true);
 #pragma unroll
@@ -419,31 +531,12 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         }
         stage_end();
       }
-      // residual (this thread's own row, columns [64h, 64h+64)): first half in flight during the ctr2 MMAs
-      const int64_t m = m0 + r;
-      const bool live = m < M;
-      const float4* resp = reinterpret_cast<const float4*>(X + (live ? m : 0) * LGCN_C + h * 64);
-      float4 r4[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      drain_gn(gam + 1024, false);
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          f[cb * 32 + 4 * c] = fmaxf(f[cb * 32 + 4 * c] + r4[c].x, 0.f);
-          f[cb * 32 + 4 * c + 1] = fmaxf(f[cb * 32 + 4 * c + 1] + r4[c].y, 0.f);
-          f[cb * 32 + 4 * c + 2] = fmaxf(f[cb * 32 + 4 * c + 2] + r4[c].z, 0.f);
-          f[cb * 32 + 4 * c + 3] = fmaxf(f[cb * 32 + 4 * c + 3] + r4[c].w, 0.f);
-        }
-        if (cb == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      store_out(m0);
+      pending = true;
+      pending_m0 = m0;
     }
+    if (pending) finish_tile(pending_m0);
     if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");   // prefetches past the last tile (zero-filled)
   }
 
   tc_fence_before();
@@ -521,6 +614,7 @@ k_multi_sum(const float* __restrict__ X, const int32_t* __restrict__ hdr, const 
 }
 
 bool g_attr_set = false;
+long long* g_timeline = nullptr;
 
 struct PlanView {
   int32_t* hdr;
@@ -568,6 +662,14 @@ extern "C" int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* co
   return 0;
 }
 
+// profiling aid (tools/timeline_fused.py): device buffer [1024][8] of clock64 stamps written by CTA 0 when debug flag
+// 256 is set.  Columns: MMA warp {weights ready, A ready, issued}, producer warp 4 {stage start, chunk in registers,
+// A slot free, stored + published}.
+extern "C" int lgcn_debug_timeline(long long* device_buffer) {
+  g_timeline = device_buffer;
+  return 0;
+}
+
 int64_t lgcn_laneconv_fused_aux_bytes(int64_t n_edges) { return lgcn_align_up((n_edges / 2 + 1) * LGCN_C * 4, 1024); }
 
 // out[m] = one LaneConv block of x (chain = 1) or relu(GN(sum_k W_k agg_k)) (chain = 0).  w_hi / w_lo: pre-split
@@ -593,6 +695,7 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
   FusedArgs a;
   a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.n_keys = n_keys; a.chain = chain; a.dbg = lgcn_debug_get();
+  a.tl = g_timeline;
   const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
   k_laneconv_fused<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);

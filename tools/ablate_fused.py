@@ -1,6 +1,6 @@
 """Ablation timing of the aggregate-first LaneConv kernel (laneconv_fused.cu) on the GPU box, on the real synthetic
 batch-128 lane graph: one block (n_blocks = 1) under the lgcn_debug_flags switches
-(1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion / tcgen05.st, 64 no accumulator flushes)."""
+(1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion / tcgen05.st, 64 no accumulator flushes, 128 no weight TMA)."""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -45,5 +45,6 @@ def t(flags, n=6):
 print(f"nodes {M} edges {pg.n_edges}; us per block (split + multi_sum + fused kernel + final copy)")
 for name, fl in [("full", 0), ("no stores", 1), ("no flushes", 64), ("no loads", 8), ("no loads, no conversion", 8 | 32),
                  ("no MMAs", 4), ("no MMAs, no loads", 4 | 8), ("no MMAs, no loads, no conversion", 4 | 8 | 32),
-                 ("skeleton: + no flushes, no stores", 4 | 8 | 32 | 64 | 1), ("no conversion only", 32)]:
+                 ("skeleton: + no flushes, no stores", 4 | 8 | 32 | 64 | 1), ("no conversion only", 32), ("no weight TMA", 128), ("MMAs only: no weight TMA, no loads, no conversion", 128 | 8 | 32),
+                 ("A feed only: no weight TMA, no MMAs", 128 | 4), ("barriers only", 128 | 4 | 8 | 32 | 64 | 1)]:
     print(f"{name:45s} {t(fl):8.1f}")
