@@ -21,6 +21,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HAVE_TC = int(os.path.exists(os.path.join(CSRC, "gemm_tc.cu")))
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          f"-DLGCN_HAVE_TC={HAVE_TC}", f"-DLGCN_DEFAULT_ENGINE={HAVE_TC}"]
+FLAGS += os.environ.get("LGCN_NVCC_EXTRA", "").split()   # e.g. -DLGCN_TIMELINE for tools/timeline_fused.py
 
 
 def _deps(src):

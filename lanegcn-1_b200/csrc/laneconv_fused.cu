@@ -33,6 +33,10 @@ using namespace tc;
 
 namespace {
 
+#ifndef LGCN_FUSED_WAIT
+#define LGCN_FUSED_WAIT mbar_spin
+#endif
+
 constexpr int kTileM = 128;
 constexpr int kWStages = 4;
 constexpr int kXStages = 3;                                  // raw fp32 A chunks in flight (cp.async ring)
@@ -120,7 +124,14 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
   const bool chain = a.chain != 0;
   const int dbg = a.dbg;
+#ifdef LGCN_TIMELINE
   long long* tl = (blockIdx.x == 0 && (dbg & 256)) ? a.tl : nullptr;
+#define LGCN_TL_MMA(c) if (tl && tls < 1024) tl[tls * 8 + (c)] = clock64()
+#define LGCN_TL_PROD(c) if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + (c)] = clock64()
+#else
+#define LGCN_TL_MMA(c) (void)0
+#define LGCN_TL_PROD(c) (void)0
+#endif
   const int flush_keys = (dbg & 64) ? (1 << 20) : kFlushKeys;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
   const int64_t grid = gridDim.x;
@@ -133,7 +144,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
       for (int kk = 0; kk < keys_per_tile; ++kk) {
         for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(bar_empty + 8 * ws, phase ^ 1);
+          LGCN_FUSED_WAIT(bar_empty + 8 * ws, phase ^ 1);
           if (elect_one()) {
             const uint32_t bar = bar_full + 8 * ws, dst = sbase + ws * kWStageBytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWStageBytes) : "memory");
@@ -171,7 +182,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       int64_t stages_left = my_tiles * keys_per_tile * 4;
       asm volatile(".reg .pred lgcn_peek;");
       if (stages_left > 0) {
-        mbar_wait(bar_full, 0);
+        LGCN_FUSED_WAIT(bar_full, 0);
         tc_fence_after();
       }
       const uint32_t d_main = tmem_base + kColMain, d_cross = tmem_base + kColCross;
@@ -180,11 +191,16 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         for (int kk = 0; kk < keys_per_tile; ++kk) {
           const bool fresh_all = kk == 0 || kk == nk;                     // projections / ctr2 start
           const bool fresh_main = fresh_all || since == flush_keys;       // main restarts after a flush
+          // after a flush only MAIN restarts: the cross-term MMAs of the first stage are issued before waiting for the
+          // producers to have read main, so the tensor pipe has 8 instructions of work during the flush
+          const bool late_wait = fresh_main && !fresh_all && !(dbg & 4);
           if (fresh_main) {
             since = 0;
-            mbar_wait(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have read the accumulator(s)
-            ++acc_uses;
-            tc_fence_after();
+            if (!late_wait) {
+              LGCN_FUSED_WAIT(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have read the accumulators
+              ++acc_uses;
+              tc_fence_after();
+            }
           }
           ++since;
           const bool publish = kk >= nk - 1 || since == flush_keys;       // a flush / drain follows this key
@@ -199,27 +215,40 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
               ph2 ^= 1;
             }
             --stages_left;
-            if (tl && tls < 1024) tl[tls * 8 + 0] = clock64();
+            LGCN_TL_MMA(0);
             asm volatile("mbarrier.test_wait.parity.shared::cta.b64 lgcn_peek, [%0], %1;" ::"r"(bar_full + 8 * st2), "r"(ph2)
                          : "memory");
+            if (kc == 0 && late_wait) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (dbg & 4) break;
-              const bool k0 = kc == 0 && j == 0;
-              umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_all && k0) ? 0u : 1u);
-              umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
-              umma_tf32_ts(d_main, a_hi + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_main && k0) ? 0u : 1u);
+              for (int j = 0; j < 4; ++j) {
+                umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, 1u);
+                umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
+              }
+              LGCN_FUSED_WAIT(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have added main to their sums
+              ++acc_uses;
+              tc_fence_after();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(d_main, a_hi + 8 * j, umma_desc(w_hi + j * 32), kIdesc, j ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (dbg & 4) break;
+                const bool k0 = kc == 0 && j == 0;
+                umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_all && k0) ? 0u : 1u);
+                umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
+                umma_tf32_ts(d_main, a_hi + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_main && k0) ? 0u : 1u);
+              }
             }
             umma_commit(bar_empty + 8 * st);
             if (publish && kc == 3) umma_commit(bar_acc_full);
-            if (tl && tls < 1024) tl[tls * 8 + 1] = clock64();
+            LGCN_TL_MMA(1);
             uint32_t ready;
             asm volatile("selp.u32 %0, 1, 0, lgcn_peek;" : "=r"(ready));
             if (stages_left > 0) {
-              if (!ready) mbar_wait(bar_full + 8 * st2, ph2);
+              if (!ready) LGCN_FUSED_WAIT(bar_full + 8 * st2, ph2);
               tc_fence_after();
             }
-            if (tl && tls < 1024) tl[tls * 8 + 2] = clock64();
+            LGCN_TL_MMA(2);
             ++tls;
             st = st2;
             phase = ph2;
@@ -317,7 +346,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
     };
     auto stage_begin = [&]() {
-      mbar_wait(bar_empty + 8 * as, a_phase ^ 1);
+      LGCN_FUSED_WAIT(bar_empty + 8 * as, a_phase ^ 1);
       tc_fence_after();
     };
     auto stage_end = [&]() {
@@ -333,7 +362,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     // f[64] = columns [64h, 64h+64) of this thread's row: running fp32 sum of the flushed main accumulator
     float f[64];
     auto acc_wait = [&]() {
-      mbar_wait(bar_acc_full, acc_uses & 1);
+      LGCN_FUSED_WAIT(bar_acc_full, acc_uses & 1);
       ++acc_uses;
       tc_fence_after();
     };
@@ -354,7 +383,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
       acc_release();
     };
-    auto drain_gn = [&](uint32_t gb, bool add) {   // gb: shared address of gamma (beta 512 B behind it) for this half
+    auto drain = [&](bool add) {   // f (+)= main + cross, then the accumulators are released to the MMA warp
       acc_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -369,6 +398,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         }
       }
       acc_release();
+    };
+    auto gn = [&](uint32_t gb) {   // GroupNorm(1) of the row; gb: shared address of gamma (beta 512 B behind it)
       float s1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; ++c) s1 += f[c];
@@ -430,31 +461,33 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     for (int s0 = 0; s0 < kXStages; ++s0) issue(vr, s0, s0);   // stages 0..2 = chunks 0..2 of key 0 (kXStages <= 4)
     int xs = 0;   // ring slot of the stage being converted
     int tls = 0;
-    // second epilogue of a tile (ctr2 accumulators -> GroupNorm + residual + ReLU -> store).  It runs three stages
+    // Second epilogue of a tile (ctr2 accumulators -> GroupNorm + residual + ReLU -> store).  It runs three stages
     // into the NEXT tile: those stages are produced while the ctr2 MMAs still execute, the accumulators are drained
     // the moment ctr2 retires, and the tensor pipe then has three stages of queued work while the norm, the residual
-    // and the stores are done (a first version finished the tile first and idled the pipe ~7 k cycles per tile).
+    // and the stores are done.  (Finishing the tile first idled the pipe ~7 k cycles per tile; spreading the epilogue
+    // over four later stages was slower still: the producers are not far enough ahead; direct 16-byte global stores
+    // instead of the staged TMA store took 2.0 k cycles instead of 1.6 k.  tools/timeline_fused.py.)
     auto finish_tile = [&](int64_t pm0) {
       const int64_t m = pm0 + r;
       const bool live = m < M;
       const float4* resp = reinterpret_cast<const float4*>(X + (live ? m : 0) * LGCN_C + h * 64);
-      float4 r4[8];
+      float4 ra[8], rb[8];   // residual: first half requested before the drain, second half before the norm
 #pragma unroll
-      for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      drain_gn(gam + 1024, false);
+      for (int c = 0; c < 8; ++c) ra[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      drain(false);
 #pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
+      for (int c = 0; c < 8; ++c) rb[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gn(gam + 1024);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          f[cb * 32 + 4 * c] = fmaxf(f[cb * 32 + 4 * c] + r4[c].x, 0.f);
-          f[cb * 32 + 4 * c + 1] = fmaxf(f[cb * 32 + 4 * c + 1] + r4[c].y, 0.f);
-          f[cb * 32 + 4 * c + 2] = fmaxf(f[cb * 32 + 4 * c + 2] + r4[c].z, 0.f);
-          f[cb * 32 + 4 * c + 3] = fmaxf(f[cb * 32 + 4 * c + 3] + r4[c].w, 0.f);
-        }
-        if (cb == 0) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) r4[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int c = 0; c < 8; ++c) {
+        f[4 * c] = fmaxf(f[4 * c] + ra[c].x, 0.f);
+        f[4 * c + 1] = fmaxf(f[4 * c + 1] + ra[c].y, 0.f);
+        f[4 * c + 2] = fmaxf(f[4 * c + 2] + ra[c].z, 0.f);
+        f[4 * c + 3] = fmaxf(f[4 * c + 3] + ra[c].w, 0.f);
+        f[32 + 4 * c] = fmaxf(f[32 + 4 * c] + rb[c].x, 0.f);
+        f[33 + 4 * c] = fmaxf(f[33 + 4 * c] + rb[c].y, 0.f);
+        f[34 + 4 * c] = fmaxf(f[34 + 4 * c] + rb[c].z, 0.f);
+        f[35 + 4 * c] = fmaxf(f[35 + 4 * c] + rb[c].w, 0.f);
       }
       store_out(pm0);
     };
@@ -480,24 +513,26 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
             for (int c = 0; c < 64; ++c) f[c] = 0.f;
           }
           float4 cur[4];
-          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 3] = clock64();
+          LGCN_TL_PROD(3);
           take(cur, xs);
-          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 4] = clock64();
+          LGCN_TL_PROD(4);
+          stage_begin();
+          LGCN_TL_PROD(5);
+          if (!(dbg & 32)) put16(cur, h * 16);
+          stage_end();
+          LGCN_TL_PROD(6);
+          ++tls;
+          // off the publish path: sources of the next key, then refill the slot with stage + 3 (chunk kc+3 of this
+          // key when kc == 0, else chunk kc-1 of the next key)
           if (kc == 0) {
             // all groups but the two newest have landed: the entry of key kk+1 (requested a key ago) is readable
             sources((int)t, kk + 1, (kseq + 1) & 3, vrn);
             request((int)t, kk + 2, (kseq + 2) & 3);   // joins this stage's group
+            issue(vr, 3, xs);
+          } else {
+            issue(vrn, kc - 1, xs);
           }
-          // refill the slot with stage + 3: chunk kc+3 of this key (kc == 0) or chunk kc-1 of the next key
-          if (kc == 0) issue(vr, 3, xs);
-          else issue(vrn, kc - 1, xs);
           if (++xs == kXStages) xs = 0;
-          stage_begin();
-          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 5] = clock64();
-          if (!(dbg & 32)) put16(cur, h * 16);
-          stage_end();
-          if (tl && e == 0 && lane == 0 && tls < 1024) tl[tls * 8 + 6] = clock64();
-          ++tls;
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
           // warp resumes
           if (kc == 2 && flush_here) flush_main();
@@ -506,7 +541,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         for (int i = 0; i < 4; ++i) vr[i] = vrn[i];
         kseq = (kseq + 1) & 3;
       }
-      drain_gn(gam, true);
+      drain(true);
+      gn(gam);
 #pragma unroll
       for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
       if (!chain) {

@@ -52,3 +52,14 @@ d = np.diff(t[:704, 2])
 for s0 in range(64, 192, 16):
     print(f"{s0:4d}: " + " ".join(f"{int(x):5d}" for x in d[s0:s0 + 16]))
 print("tile totals:", [int(t[64 * (i + 1), 2] - t[64 * i, 2]) for i in range(1, 9)])
+
+nz = np.nonzero(t[:1000, 7])[0]
+if len(nz) >= 8:
+    k = nz[4]
+    print("\nsecond epilogue of one tile (producer warp 4), cycles: start -> drained+normed -> residual added -> stored")
+    print("  ", [int(t[k + i, 7] - t[k, 7]) for i in range(4)], " | last tile: acc_full seen -> accumulators released:", int(t[1017, 7] - t[1016, 7]),
+          " finish start -> acc_full seen:", int(t[1016, 7] - t[nz[-4], 7]))
+
+print("\nMMA thread, stages 76..92: issue (12 MMAs + commit) | wait for the next stage | total")
+for s_ in range(76, 92):
+    print(f"  {s_:4d} kc={s_ % 4}: {int(t[s_, 1] - t[s_, 0]):6d} {int(t[s_, 2] - t[s_, 1]):6d} {int(t[s_ + 1, 0] - t[s_, 0]):6d}")
