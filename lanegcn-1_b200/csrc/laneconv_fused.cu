@@ -132,7 +132,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
 #define LGCN_TL_MMA(c) (void)0
 #define LGCN_TL_PROD(c) (void)0
 #endif
-  const int flush_keys = (dbg & 64) ? (1 << 20) : kFlushKeys;
+  const int flush_keys = (dbg & 64) ? (1 << 20) : (dbg & 512) ? 5 : kFlushKeys;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
   const int64_t grid = gridDim.x;
   const int keys_per_tile = nk + (chain ? 1 : 0);   // key nk = ctr2 (weights follow the projections in w_hi / w_lo)
@@ -400,16 +400,26 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       acc_release();
     };
     auto gn = [&](uint32_t gb) {   // GroupNorm(1) of the row; gb: shared address of gamma (beta 512 B behind it)
-      float s1 = 0.f;
+      // four independent partial sums: a single 64-long dependent chain costs ~4 cycles per element
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 64; ++c) s1 += f[c];
-      const float mean_h = s1 * (1.0f / 64.0f);
-      float m2_h = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float d = f[c] - mean_h;
-        m2_h = fmaf(d, d, m2_h);
+      for (int c = 0; c < 64; c += 4) {
+        s4[0] += f[c];
+        s4[1] += f[c + 1];
+        s4[2] += f[c + 2];
+        s4[3] += f[c + 3];
       }
+      const float mean_h = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 64.0f);
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float d0 = f[c] - mean_h, d1 = f[c + 1] - mean_h, d2 = f[c + 2] - mean_h, d3 = f[c + 3] - mean_h;
+        q4[0] = fmaf(d0, d0, q4[0]);
+        q4[1] = fmaf(d1, d1, q4[1]);
+        q4[2] = fmaf(d2, d2, q4[2]);
+        q4[3] = fmaf(d3, d3, q4[3]);
+      }
+      const float m2_h = (q4[0] + q4[1]) + (q4[2] + q4[3]);
       st_shared_f2(stat_mine, mean_h, m2_h);
       named_bar_sync(1 + q, 64);
       const float2 o = ld_shared_f2(stat_other);
@@ -506,7 +516,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         ++since;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
-          if (kc == 3 && kk == 0 && pending) {   // before stage 3 of the new tile
+          if (kc == 3 && kk == 0 && pending) {   // before stage 3 of the new tile (before stage 4 measured slower)
             finish_tile(pending_m0);
             pending = false;
 #pragma unroll
