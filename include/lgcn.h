@@ -52,7 +52,8 @@ int64_t lgcn_launch_count(void);
 /* Per-kernel timing for the benchmark: while enabled, lgcn_laneconv_stack / lgcn_att_forward bracket their
  * launches with CUDA events on the launching stream.  lgcn_prof_collect SYNCHRONISES on those events, returns
  * summed milliseconds and launch counts per kind (0 wide projection GEMM, 1 LaneConv gather, 2 ctr2 linear,
- * 3 whole Att layer; arrays of 4) and resets.  lgcn_prof_enable returns the previous state. */
+ * 3 whole Att layer, 4 aggregate-first LaneConv block incl. its multi-source pre-pass; ARRAYS OF 8, the rest
+ * reserved) and resets.  lgcn_prof_enable returns the previous state. */
 int lgcn_prof_enable(int on);
 int lgcn_prof_collect(double* h_ms_by_kind, int64_t* h_launches_by_kind);
 

@@ -225,7 +225,7 @@ extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_ed
     const float* src = (i & 1) ? other : feat;
     float* dst = (i & 1) ? feat : other;
     if (int rc = lgcn_split_tf32(w, w_hi, w_lo, (int64_t)(nb + 1) * CC, st)) return rc;
-    LgcnProfScope ps(LGCN_PROF_WIDE, st);
+    LgcnProfScope ps(LGCN_PROF_FUSED, st);
     if (int rc = lgcn_launch_laneconv_fused(src, dst, plan, n_nodes, n_edges, n_keys, w_hi, w_lo, gn, xa, 1, st)) return rc;
   }
   if (n_blocks & 1) LGCN_CUDA_OK(cudaMemcpyAsync(feat, other, n_nodes * LGCN_C * 4, cudaMemcpyDeviceToDevice, st));

@@ -36,7 +36,7 @@ void lgcn_count_launch();
   } while (0)
 
 // optional per-kernel timing (lgcn_prof_*): CUDA events recorded on the launching stream around a launch
-enum { LGCN_PROF_WIDE = 0, LGCN_PROF_GATHER = 1, LGCN_PROF_CTR2 = 2, LGCN_PROF_ATT = 3, LGCN_PROF_KINDS = 4 };
+enum { LGCN_PROF_WIDE = 0, LGCN_PROF_GATHER = 1, LGCN_PROF_CTR2 = 2, LGCN_PROF_ATT = 3, LGCN_PROF_FUSED = 4, LGCN_PROF_KINDS = 8 };
 struct LgcnProfScope {
   int slot;
   cudaStream_t st;

@@ -418,6 +418,21 @@ def test_net_forward_matches_reference_golden(cuda, lib, net, engine, name):
     assert [len(x) for x in out["cls"]] == [len(s["ctrs"]) for s in golden_scenes(name)]
 
 
+def test_prefetch_forward_equals_forward(cuda, lib, net):
+    """The pipelined entry point (staging of batch i+1 overlapped with batch i) returns exactly what Net.forward
+    returns, batch by batch, for batches of different shapes."""
+    batches = [synth.collate(synth.make_scenes(b, "tiny", seed0=s)) for b, s in ((3, 0), (1, 7), (4, 11), (2, 3))]
+    want = [net(b) for b in batches]
+    got = list(L.prefetch_forward(net, iter(batches)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in ("cls", "reg"):
+            assert len(g[k]) == len(w[k])
+            for a, b in zip(g[k], w[k]):
+                assert torch.equal(a, b)
+    assert list(L.prefetch_forward(net, iter([]))) == []
+
+
 def test_net_forward_matches_oracle_batch8(cuda, lib, net):
     scenes = synth.make_scenes(8, "small", seed0=20)
     sd = weights()

@@ -47,7 +47,7 @@ def stack_times(n=5):
         lib.lgcn_prof_enable(1)
         _C.check(lib.lgcn_laneconv_stack(feat.data_ptr(), rowptr.data_ptr(), col.data_ptr(), K, 1, wpack.data_ptr(), M, ws.data_ptr(), sp))
         lib.lgcn_prof_enable(0)
-        ms, cnt = (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)()
+        ms, cnt = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
         _C.check(lib.lgcn_prof_collect(ms, cnt))
         cur = [ms[0] * 1e3, ms[1] * 1e3, ms[2] * 1e3]
         if it:
