@@ -909,6 +909,14 @@ class Net(nn.Module):
                 for t in (b.graphs.fl, b.graphs.local, b.graphs.segs, b.graphs.off_dev, b.actors, b.rot_a, b.orig_a,
                           b.actor_ctrs.cat, b.actor_ctrs.off_dev):
                     t.record_stream(cur)  # allocated on the copy stream, consumed here
+            # ActorNet (stock PyTorch, CUDA-graphed, independent of the map) goes to a side stream FIRST: its ~1.3 ms
+            # of device work covers the host time of the graph / pair-list launches below (the device used to idle
+            # ~1 ms at the start of every forward waiting for them; tools/trace_step.py)
+            cur, side = torch.cuda.current_stream(), _side_stream(b.actors.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                x = b.actors.transpose(1, 2).contiguous()
+                actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
             actor_ctrs = b.actor_ctrs
             sizes = [len(x) for x in actor_ctrs]
             actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev)
@@ -920,16 +928,10 @@ class Net(nn.Module):
                 (actor_ctrs, node_ctrs, cfg["map2actor_dist"]),
                 (actor_ctrs, actor_ctrs, cfg["actor2actor_dist"]),
             ])
-            # ... enqueue MapNet (a handful of C-ABI calls, milliseconds of device work) and ActorNet (stock PyTorch,
-            # independent of the map, on a side stream) ...
-            cur, side = torch.cuda.current_stream(), _side_stream(b.actors.device)
-            side.wait_stream(cur)
+            # ... enqueue MapNet (a handful of C-ABI calls, milliseconds of device work) ...
             counted = torch.cuda.Event()
             counted.record(cur)
             nodes, node_idcs, node_ctrs = self.map_net(graph)                     # :135
-            with torch.cuda.stream(side):
-                x = b.actors.transpose(1, 2).contiguous()
-                actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
             # ... and only now take the ONE host synchronisation of the forward (three pair totals), on an auxiliary
             # stream that waits for the count kernels only: the device stays busy with MapNet meanwhile.
             p_a2m, p_m2a, p_a2a = fill_pair_lists(pls, counted=counted)
