@@ -349,6 +349,19 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       LGCN_FUSED_WAIT(bar_empty + 8 * as, a_phase ^ 1);
       tc_fence_after();
     };
+    // the same wait split in two: the (non-blocking) test is issued before the chunk is read from shared memory and
+    // its predicate consumed afterwards, so the barrier round trip overlaps the shared-memory latency
+    asm volatile(".reg .pred lgcn_peek_a;");
+    auto stage_peek = [&]() {
+      asm volatile("mbarrier.test_wait.parity.shared::cta.b64 lgcn_peek_a, [%0], %1;" ::"r"(bar_empty + 8 * as), "r"(a_phase ^ 1)
+                   : "memory");
+    };
+    auto stage_begin_peeked = [&]() {
+      uint32_t ready;
+      asm volatile("selp.u32 %0, 1, 0, lgcn_peek_a;" : "=r"(ready));
+      if (!ready) LGCN_FUSED_WAIT(bar_empty + 8 * as, a_phase ^ 1);
+      tc_fence_after();
+    };
     auto stage_end = [&]() {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -524,23 +537,23 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           }
           float4 cur[4];
           LGCN_TL_PROD(3);
+          stage_peek();
           take(cur, xs);
           LGCN_TL_PROD(4);
-          stage_begin();
+          stage_begin_peeked();
           LGCN_TL_PROD(5);
           if (!(dbg & 32)) put16(cur, h * 16);
+          // refill the slot with stage + 3 (chunk kc-1 of the next key) while the tcgen05.st complete; at kc == 0 the
+          // sources of the next key come first, and that longer sequence runs after the publish instead
+          if (kc != 0) issue(vrn, kc - 1, xs);
           stage_end();
           LGCN_TL_PROD(6);
           ++tls;
-          // off the publish path: sources of the next key, then refill the slot with stage + 3 (chunk kc+3 of this
-          // key when kc == 0, else chunk kc-1 of the next key)
           if (kc == 0) {
             // all groups but the two newest have landed: the entry of key kk+1 (requested a key ago) is readable
             sources((int)t, kk + 1, (kseq + 1) & 3, vrn);
             request((int)t, kk + 2, (kseq + 2) & 3);   // joins this stage's group
-            issue(vr, 3, xs);
-          } else {
-            issue(vrn, kc - 1, xs);
+            issue(vr, 3, xs);                          // chunk 3 of this key
           }
           if (++xs == kXStages) xs = 0;
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
