@@ -557,7 +557,9 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           }
           if (++xs == kXStages) xs = 0;
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
-          // warp resumes
+          // warp resumes.  (Handling two stages per iteration -- one cp.async wait, one tcgen05.wait::st and two
+          // independent conversion chains per pair -- was slower, 548 vs 507 us per block: the coarser hand-off costs
+          // more pipelining than the shared fixed costs save.)
           if (kc == 2 && flush_here) flush_main();
         }
 #pragma unroll
