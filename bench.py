@@ -259,11 +259,19 @@ def run_ours(args):
         return torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
 
     def run_e2e(n):
+        trace = os.environ.get("LGCN_E2E_TRACE") == "1"
+        tt = [time.perf_counter()]
         for out in L.prefetch_forward(net, (data for _ in range(n))):
             res = finish(out)
+            if trace:
+                tt.append(time.perf_counter())
+        if trace:
+            print("e2e per-batch ms:", " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip(tt, tt[1:])), file=sys.stderr)
         return res
 
-    run_e2e(3)
+    # warm-up: the staged tensors are allocated on the copy stream and released on the compute stream, and the caching
+    # allocator keeps calling cudaMalloc until it owns enough blocks to rotate (per-batch times settle after ~12 batches)
+    run_e2e(max(args.warmup, 16))
     sync_all()
     t0 = time.perf_counter()
     for _ in range(5):

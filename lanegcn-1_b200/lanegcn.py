@@ -13,6 +13,7 @@ There is no CPU path: tensors must live on a CUDA device and the library must be
 from __future__ import annotations
 
 import ctypes
+import operator
 import os
 from typing import Dict, List, Optional
 
@@ -308,7 +309,7 @@ def stage_graphs(graphs: List[dict], extra_float: Optional[List[Tensor]] = None,
     dev = _target_device(graphs[0]["feats"])
     parts = []
     for key in ("ctrs", "feats", "turn", "control", "intersect"):
-        parts += [g[key].reshape(-1) for g in graphs]
+        parts += [g[key] for g in graphs]   # any shape: _stage_cat flattens in order
     n_extra = len(extra_float) if extra_float else 0
     if n_extra:
         parts += extra_float
@@ -324,7 +325,7 @@ def stage_graphs(graphs: List[dict], extra_float: Optional[List[Tensor]] = None,
     if any(t.dim() == 0 for t in locs[-4 * B:]):  # pickles where an empty left/right array collapsed to a scalar
         locs = [t.new_zeros(0) if t.dim() == 0 else t for t in locs]                   # (lanegcn.py:204-207)
     dt = locs[0].dtype
-    if {t.dtype for t in locs} != {dt}:
+    if set(map(_DTYPE, locs)) != {dt}:
         dt, locs = torch.int64, [t.long() for t in locs]
     if dt not in (torch.int16, torch.int32, torch.int64):
         raise RuntimeError(f"lanegcn_b200: edge indices must be int16/int32/int64, got {dt}")
@@ -422,17 +423,25 @@ class _PinnedPool:
         return ring, i, buf
 
 
+_DATA_PTR = operator.methodcaller("data_ptr")
+_IS_CONTIG = operator.methodcaller("is_contiguous")
+_DTYPE = operator.attrgetter("dtype")
+_NBYTES = operator.attrgetter("nbytes")
+
+
 def _stage_cat(parts: List[Tensor], dev, dtype, tag: str) -> Tensor:
-    """Concatenate 1-D CPU tensors straight into a pinned buffer and issue ONE async H2D copy; returns the device
-    tensor and the per-part byte sizes.  Device inputs are concatenated on the device."""
+    """Concatenate CPU tensors (any shape, flattened in order) straight into a pinned buffer and issue ONE async H2D
+    copy; returns the flat device tensor and the per-part byte sizes.  Device inputs are concatenated on the device.
+    A batch is ~5 k small tensors, so the per-tensor Python work is kept to four C-level passes (map + methodcaller:
+    ~70 ns per element each; generator expressions and per-tensor reshape() cost 3.5 ms per batch before)."""
     if parts[0].is_cuda:
         out = torch.cat([p.to(dtype).reshape(-1) for p in parts])
         return out, np.fromiter((p.numel() * out.element_size() for p in parts), np.int64, len(parts))
-    if {p.dtype for p in parts} != {dtype} or not all(p.is_contiguous() for p in parts):
+    if set(map(_DTYPE, parts)) != {dtype} or not all(map(_IS_CONTIG, parts)):
         parts = [p.to(dtype).contiguous() for p in parts]
     k = len(parts)
-    sizes = np.fromiter((p.nbytes for p in parts), np.int64, k)
-    ptrs = np.fromiter((p.data_ptr() for p in parts), np.uint64, k)
+    sizes = np.array(list(map(_NBYTES, parts)), np.int64)
+    ptrs = np.array(list(map(_DATA_PTR, parts)), np.uint64)
     nbytes = int(sizes.sum())
     n = nbytes // parts[0].element_size()
     ring, i, buf = _PinnedPool.take(tag, nbytes)
@@ -877,8 +886,7 @@ class Net(nn.Module):
                 cnt = torch.tensor(sizes, device=dev)
                 off_dev = torch.tensor(aoff, dtype=torch.int32, device=dev)
             else:
-                extra = ([x.reshape(-1) for x in data["feats"]] + [x.reshape(-1) for x in data["ctrs"]]
-                         + [x.reshape(-1) for x in data["rot"]] + [x.reshape(-1) for x in data["orig"]])
+                extra = list(data["feats"]) + list(data["ctrs"]) + list(data["rot"]) + list(data["orig"])
                 sg = stage_graphs(data["graph"], extra_float=extra, extra_i32=aoff, extra_i64=sizes)
                 fl = sg.extra_float
                 b.actors = fl[: 60 * A].view(A, 20, 3)
