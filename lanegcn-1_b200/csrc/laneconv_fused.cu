@@ -559,7 +559,9 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
           // warp resumes.  (Handling two stages per iteration -- one cp.async wait, one tcgen05.wait::st and two
           // independent conversion chains per pair -- was slower, 548 vs 507 us per block: the coarser hand-off costs
-          // more pipelining than the shared fixed costs save.)
+          // more pipelining than the shared fixed costs save.  Two producer TEAMS -- warps 4-7 / 8-11 producing the
+          // stages of one parity each, whole 32-float chunks, 5 arrivals per stage -- was slower too, 560 us, and so
+          // was its barrier skeleton: the per-warp instruction stream is not what bounds the feed.)
           if (kc == 2 && flush_here) flush_main();
         }
 #pragma unroll
