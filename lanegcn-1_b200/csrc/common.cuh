@@ -103,6 +103,7 @@ int lgcn_launch_linear(const LinearArgs& a, cudaStream_t st);     // engine disp
 int lgcn_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t st);
 int lgcn_launch_wide_tc(const LinearArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st);
 int64_t lgcn_laneconv_fused_aux_bytes(int64_t n_edges);
+int lgcn_launch_linear_fused(const LinearArgs& a, cudaStream_t st);
 int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, int64_t n_edges, int n_keys,
                                const float* w_hi, const float* w_lo, const float* gn, float* xa, int chain,
                                cudaStream_t st);

@@ -36,6 +36,8 @@
 //
 // Measured (batch 128: 193,536 rows, 2.4 M edges): 0.48 ms per block against 0.81 ms for the three split kernels;
 // DESIGN.md section 3 lists what the tuning found and what was tried and rejected.
+#include <cstring>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -81,6 +83,13 @@ struct FusedArgs {
   int64_t M;
   int n_keys;
   int chain;             // 1: ctr2 + GN + residual + ReLU inside the kernel
+  // linear mode (tab == nullptr): out = epilogue( sum_k W_k . src[k][ idx[k] ? idx[k][row] : row ] ), the generic
+  // bias-free Linear (+GroupNorm, +ReLU, +residual, +ReLU) of lgcn_linear128 with up to three K=128 sources
+  const float* src[3];
+  const int32_t* idx[3];
+  const float* res;
+  const float* beta;     // linear mode: gn = gamma, beta separate
+  int flags;             // LGCN_EPI_* (linear mode)
   long long* tl;         // timeline buffer [1024][8] (dbg & 256, CTA 0 only)
   int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes, 128 no weight loads)
 };
@@ -112,8 +121,14 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     mbar_init(bar_acc_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 4 * 128; i += kNumThreads)
-    reinterpret_cast<float*>(smem + kSmemGam)[i] = a.gn[i];
+  {
+    float* g = reinterpret_cast<float*>(smem + kSmemGam);
+    if (a.tab) {
+      for (int i = threadIdx.x; i < 4 * 128; i += kNumThreads) g[i] = a.gn[i];
+    } else if (a.gn && threadIdx.x < 256) {
+      g[threadIdx.x] = threadIdx.x < 128 ? a.gn[threadIdx.x] : a.beta[threadIdx.x - 128];
+    }
+  }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(tmem_slot)),
@@ -130,6 +145,15 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const float* __restrict__ X = a.X;
   const float* __restrict__ XA = a.XA;
   const int32_t* __restrict__ tab = a.tab;
+  const bool linear = a.tab == nullptr;
+  const float* __restrict__ src0 = a.src[0];
+  const float* __restrict__ src1 = a.src[1];
+  const float* __restrict__ src2 = a.src[2];
+  const int32_t* __restrict__ idx0 = a.idx[0];
+  const int32_t* __restrict__ idx1 = a.idx[1];
+  const int32_t* __restrict__ idx2 = a.idx[2];
+  const float* __restrict__ lin_res = a.res;
+  const int lin_flags = a.flags;
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
   const bool chain = a.chain != 0;
   const int dbg = a.dbg;
@@ -293,31 +317,42 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       const int64_t m = (int64_t)t * kTileM + r;
       return (t < n_tiles_i && m < M) ? (int)m : -1;
     };
+    auto key_idx = [&](int kk) -> const int32_t* { return kk == 0 ? idx0 : kk == 1 ? idx1 : idx2; };
     auto request = [&](int t, int kk, int ring) {   // joins the cp.async group of the current stage
       key_norm(t, kk);
-      if (kk > 0 && t < n_tiles_i) {
-        const int32_t* src = tab + (((int64_t)t * n_keys + (kk - 1)) << 7) + r;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(slot0 + 1024u * ring), "l"(src) : "memory");
+      if (t >= n_tiles_i) return;
+      const int32_t* src = nullptr;
+      if (linear) {
+        const int32_t* ix = key_idx(kk);
+        const int64_t m = (int64_t)t * kTileM + r;
+        if (ix && m < M) src = ix + m;
+      } else if (kk > 0) {
+        src = tab + (((int64_t)t * n_keys + (kk - 1)) << 7) + r;
       }
+      if (src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(slot0 + 1024u * ring), "l"(src) : "memory");
     };
     // sources of the four rows this lane fetches for (tile t, key kk): rows 8i + (lane >> 2) of the warp's block
     auto sources = [&](int t, int kk, int ring, int (&vr)[4]) {
       key_norm(t, kk);
       int v = -1;
       if (t < n_tiles_i) {
-        if (kk == 0) v = self_src(t);
-        else asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot0 + 1024u * ring) : "memory");
+        const bool own = linear ? key_idx(kk) == nullptr : kk == 0;
+        v = self_src(t);
+        if (!own && v >= 0) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot0 + 1024u * ring) : "memory");
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) vr[i] = __shfl_sync(0xffffffffu, v, 8 * i + (lane >> 2));
     };
     const uint32_t piece = lane & 3;
-    auto issue = [&](const int (&vr)[4], int kc, int slot) {   // 4 x 16 B per lane; one commit group per stage
+    // kk: the key the rows belong to (selects the source matrix in linear mode; may be nk = key 0 of the next tile)
+    auto issue = [&](const int (&vr)[4], int kc, int slot, int kk) {   // 4 x 16 B per lane; one commit group per stage
+      if (kk >= nk) kk -= nk;
+      const float* base = !linear ? X : kk == 0 ? src0 : kk == 1 ? src1 : src2;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int v = vr[i];
         const int row = 8 * i + (lane >> 2);
-        const float* p = v >= 0 ? X + (int64_t)v * LGCN_C : XA + (int64_t)(v < -1 ? -2 - v : 0) * LGCN_C;
+        const float* p = v >= 0 ? base + (int64_t)v * LGCN_C : XA + (int64_t)(v < -1 ? -2 - v : 0) * LGCN_C;
         const uint32_t dst = xblk + slot * 16384 + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
         const uint32_t n = (v != -1 && !(dbg & 8)) ? 16u : 0u;   // 0 source bytes: the 16 B are zero-filled
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p + kc * 32 + h * 16 + piece * 4), "r"(n)
@@ -484,13 +519,14 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     // prologue: table entries of keys 1 and 2, chunks of stages 0..2
     int vr[4], vrn[4];
     int kseq = 0;   // running key count & 3: ring slot of a table entry = (kseq + distance) & 3
+    request((int)blockIdx.x, 0, 0);   // (key 0 has an entry only in linear mode with a gathered first source)
     request((int)blockIdx.x, 1, 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     sources((int)blockIdx.x, 0, 0, vr);
 #pragma unroll
-    for (int s0 = 0; s0 < kXStages; ++s0) issue(vr, s0, s0);   // stages 0..2 = chunks 0..2 of key 0 (kXStages <= 4)
+    for (int s0 = 0; s0 < kXStages; ++s0) issue(vr, s0, s0, 0);   // stages 0..2 = chunks 0..2 of key 0 (kXStages <= 4)
     int xs = 0;   // ring slot of the stage being converted
     int tls = 0;
     // Second epilogue of a tile (ctr2 accumulators -> GroupNorm + residual + ReLU -> store).  It runs three stages
@@ -554,7 +590,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           if (!(dbg & 32)) put16(cur, h * 16);
           // refill the slot with stage + 3 (chunk kc-1 of the next key) while the tcgen05.st complete; at kc == 0 the
           // sources of the next key come first, and that longer sequence runs after the publish instead
-          if (kc != 0) issue(vrn, kc - 1, xs);
+          if (kc != 0) issue(vrn, kc - 1, xs, kk + 1);
           stage_end();
           LGCN_TL_PROD(6);
           ++tls;
@@ -562,7 +598,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
             // all groups but the two newest have landed: the entry of key kk+1 (requested a key ago) is readable
             sources((int)t, kk + 1, (kseq + 1) & 3, vrn);
             request((int)t, kk + 2, (kseq + 2) & 3);   // joins this stage's group
-            issue(vr, 3, xs);                          // chunk 3 of this key
+            issue(vr, 3, xs, kk);                      // chunk 3 of this key
           }
           if (++xs == kXStages) xs = 0;
           // flush of the key group that ended at kk-1: three stages late, so the A ring is full again when the MMA
@@ -576,6 +612,39 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
 #pragma unroll
         for (int i = 0; i < 4; ++i) vr[i] = vrn[i];
         kseq = (kseq + 1) & 3;
+      }
+      if (linear) {   // generic Linear epilogue: [GroupNorm] [ReLU] [+ residual] [ReLU]
+        const int64_t m = m0 + r;
+        const bool live = m < M && (lin_flags & LGCN_EPI_RES);
+        const float4* resp = reinterpret_cast<const float4*>(lin_res + (live ? m : 0) * LGCN_C + h * 64);
+        float4 ra[8], rb[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ra[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        drain(true);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rb[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lin_flags & LGCN_EPI_GN) gn(gam);
+        if (lin_flags & LGCN_EPI_RELU1) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          f[4 * c] += ra[c].x;
+          f[4 * c + 1] += ra[c].y;
+          f[4 * c + 2] += ra[c].z;
+          f[4 * c + 3] += ra[c].w;
+          f[32 + 4 * c] += rb[c].x;
+          f[33 + 4 * c] += rb[c].y;
+          f[34 + 4 * c] += rb[c].z;
+          f[35 + 4 * c] += rb[c].w;
+        }
+        if (lin_flags & LGCN_EPI_RELU2) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+        }
+        store_out(m0);
+        continue;
       }
       drain(true);
       gn(gam);
@@ -739,6 +808,80 @@ extern "C" int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* co
 // A slot free, stored + published}.
 extern "C" int lgcn_debug_timeline(long long* device_buffer) {
   g_timeline = device_buffer;
+  return 0;
+}
+
+// ------------------------------------------------------------------ linear mode: lgcn_linear128 on this kernel
+namespace {
+// W [128, n_src*128] (row stride ldw) -> hi / lo blocks [n_src*128, 128]: block k, row n = W[n, 128k .. 128k+127]
+__global__ void k_split_blocks(const float* __restrict__ w, int64_t ldw, int n_src, float* __restrict__ hi,
+                               float* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of the output
+  if (i >= n_src * 128 * 32) return;
+  const int c4 = i & 31, n = (i >> 5) & 127, k = i >> 12;
+  const float4 x = *reinterpret_cast<const float4*>(w + (int64_t)n * ldw + k * 128 + c4 * 4);
+  float4 a, b;
+  a.x = rna(x.x); b.x = rna(x.x - a.x);
+  a.y = rna(x.y); b.y = rna(x.y - a.y);
+  a.z = rna(x.z); b.z = rna(x.z - a.z);
+  a.w = rna(x.w); b.w = rna(x.w - a.w);
+  reinterpret_cast<float4*>(hi)[i] = a;
+  reinterpret_cast<float4*>(lo)[i] = b;
+}
+
+// Scratch for the split weights of a launch: a ring of device slots, each guarded by an event recorded after the
+// kernel that read it, so a slot is never rewritten (on any stream) before its last reader has finished.
+constexpr int kRing = 16;
+constexpr int64_t kSlotFloats = 2 * 3 * 128 * 128;
+float* g_ring = nullptr;
+cudaEvent_t g_ring_ev[kRing];
+bool g_ring_used[kRing];
+int g_ring_next = 0;
+}  // namespace
+
+int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
+  if (la.m <= 0) return 0;
+  LGCN_CHECK_ARG(la.n_out_blocks == 1 && la.ks == 0 && la.n_src >= 1 && la.n_src <= 3, "linear_fused: unsupported shape");
+  if (!g_attr_set) {
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    g_attr_set = true;
+  }
+  if (!g_ring) {
+    LGCN_CUDA_OK(cudaMalloc(&g_ring, kRing * kSlotFloats * sizeof(float)));
+    for (int i = 0; i < kRing; ++i) {
+      LGCN_CUDA_OK(cudaEventCreateWithFlags(&g_ring_ev[i], cudaEventDisableTiming));
+      g_ring_used[i] = false;
+    }
+  }
+  const int slot = g_ring_next;
+  g_ring_next = (g_ring_next + 1) % kRing;
+  if (g_ring_used[slot]) LGCN_CUDA_OK(cudaStreamWaitEvent(st, g_ring_ev[slot], 0));
+  float* w_hi = g_ring + slot * kSlotFloats;
+  float* w_lo = w_hi + kSlotFloats / 2;
+  const int64_t ldw = (int64_t)la.n_src * LGCN_C + la.ks;
+  k_split_blocks<<<lgcn_cdiv(la.n_src * 128 * 32, 256), 256, 0, st>>>(la.W, ldw, la.n_src, w_hi, w_lo);
+  LGCN_LAUNCH_OK();
+  CUtensorMap map, mhi, mlo;
+  if (int rc = make_out_map(&map, la.out, LGCN_C, la.m, la.ldo)) return rc;
+  if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)la.n_src * LGCN_C, LGCN_C, 32, 128)) return rc;
+  if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)la.n_src * LGCN_C, LGCN_C, 32, 128)) return rc;
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < la.n_src; ++k) {
+    a.src[k] = la.a[k];
+    a.idx[k] = la.idx[k];
+  }
+  a.X = la.a[0]; a.XA = la.a[0]; a.tab = nullptr;
+  a.gn = (la.flags & LGCN_EPI_GN) ? la.gamma : nullptr;
+  a.beta = la.beta;
+  a.res = la.res ? la.res : la.a[0];
+  a.flags = la.flags; a.M = la.m; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
+  const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
+  const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
+  k_laneconv_fused<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  LGCN_LAUNCH_OK();
+  LGCN_CUDA_OK(cudaEventRecord(g_ring_ev[slot], st));
+  g_ring_used[slot] = true;
   return 0;
 }
 
