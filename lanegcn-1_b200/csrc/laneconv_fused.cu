@@ -94,6 +94,9 @@ struct FusedArgs {
   int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes, 128 no weight loads)
 };
 
+// LINEAR = false: one LaneConv block (plan / table driven);  LINEAR = true: the generic Linear of lgcn_linear128.
+// Two instantiations so that neither hot loop carries the other mode's branches and registers.
+template <bool LINEAR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                  const __grid_constant__ CUtensorMap whi_map, const __grid_constant__ CUtensorMap wlo_map) {
@@ -123,7 +126,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   }
   {
     float* g = reinterpret_cast<float*>(smem + kSmemGam);
-    if (a.tab) {
+    if (!LINEAR) {
       for (int i = threadIdx.x; i < 4 * 128; i += kNumThreads) g[i] = a.gn[i];
     } else if (a.gn && threadIdx.x < 256) {
       g[threadIdx.x] = threadIdx.x < 128 ? a.gn[threadIdx.x] : a.beta[threadIdx.x - 128];
@@ -145,7 +148,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const float* __restrict__ X = a.X;
   const float* __restrict__ XA = a.XA;
   const int32_t* __restrict__ tab = a.tab;
-  const bool linear = a.tab == nullptr;
+  constexpr bool linear = LINEAR;
   const float* __restrict__ src0 = a.src[0];
   const float* __restrict__ src1 = a.src[1];
   const float* __restrict__ src2 = a.src[2];
@@ -559,6 +562,39 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
       store_out(pm0);
     };
+    // linear mode: the generic Linear epilogue [GroupNorm] [ReLU] [+ residual] [ReLU], deferred like finish_tile
+    auto finish_linear = [&](int64_t pm0) {
+      const int64_t m = pm0 + r;
+      const bool live = m < M && (lin_flags & LGCN_EPI_RES);
+      const float4* resp = reinterpret_cast<const float4*>(lin_res + (live ? m : 0) * LGCN_C + h * 64);
+      float4 ra[8], rb[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ra[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      drain(false);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rb[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lin_flags & LGCN_EPI_GN) gn(gam);
+      if (lin_flags & LGCN_EPI_RELU1) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        f[4 * c] += ra[c].x;
+        f[4 * c + 1] += ra[c].y;
+        f[4 * c + 2] += ra[c].z;
+        f[4 * c + 3] += ra[c].w;
+        f[32 + 4 * c] += rb[c].x;
+        f[33 + 4 * c] += rb[c].y;
+        f[34 + 4 * c] += rb[c].z;
+        f[35 + 4 * c] += rb[c].w;
+      }
+      if (lin_flags & LGCN_EPI_RELU2) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+      }
+      store_out(pm0);
+    };
     bool pending = false;
     int64_t pending_m0 = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
@@ -575,7 +611,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
           if (kc == 3 && kk == 0 && pending) {   // before stage 3 of the new tile (before stage 4 measured slower)
-            finish_tile(pending_m0);
+            if (linear) finish_linear(pending_m0);
+            else finish_tile(pending_m0);
             pending = false;
 #pragma unroll
             for (int c = 0; c < 64; ++c) f[c] = 0.f;
@@ -613,37 +650,9 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         for (int i = 0; i < 4; ++i) vr[i] = vrn[i];
         kseq = (kseq + 1) & 3;
       }
-      if (linear) {   // generic Linear epilogue: [GroupNorm] [ReLU] [+ residual] [ReLU]
-        const int64_t m = m0 + r;
-        const bool live = m < M && (lin_flags & LGCN_EPI_RES);
-        const float4* resp = reinterpret_cast<const float4*>(lin_res + (live ? m : 0) * LGCN_C + h * 64);
-        float4 ra[8], rb[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) ra[c] = live ? __ldg(resp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        drain(true);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) rb[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lin_flags & LGCN_EPI_GN) gn(gam);
-        if (lin_flags & LGCN_EPI_RELU1) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          f[4 * c] += ra[c].x;
-          f[4 * c + 1] += ra[c].y;
-          f[4 * c + 2] += ra[c].z;
-          f[4 * c + 3] += ra[c].w;
-          f[32 + 4 * c] += rb[c].x;
-          f[33 + 4 * c] += rb[c].y;
-          f[34 + 4 * c] += rb[c].z;
-          f[35 + 4 * c] += rb[c].w;
-        }
-        if (lin_flags & LGCN_EPI_RELU2) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
-        }
-        store_out(m0);
+      if (linear) {   // the epilogue runs three stages into the next tile (finish_linear below)
+        pending = true;
+        pending_m0 = m0;
         continue;
       }
       drain(true);
@@ -675,7 +684,10 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       pending = true;
       pending_m0 = m0;
     }
-    if (pending) finish_tile(pending_m0);
+    if (pending) {
+      if (linear) finish_linear(pending_m0);
+      else finish_tile(pending_m0);
+    }
     if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("cp.async.wait_all;" ::: "memory");   // prefetches past the last tile (zero-filled)
   }
@@ -843,7 +855,8 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   if (la.m <= 0) return 0;
   LGCN_CHECK_ARG(la.n_out_blocks == 1 && la.ks == 0 && la.n_src >= 1 && la.n_src <= 3, "linear_fused: unsupported shape");
   if (!g_attr_set) {
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     g_attr_set = true;
   }
   if (!g_ring) {
@@ -878,7 +891,7 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   a.flags = la.flags; a.M = la.m; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
   const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  k_laneconv_fused<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  k_laneconv_fused<true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   LGCN_LAUNCH_OK();
   LGCN_CUDA_OK(cudaEventRecord(g_ring_ev[slot], st));
   g_ring_used[slot] = true;
@@ -895,7 +908,8 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   if (n_nodes <= 0) return 0;
   LGCN_CHECK_ARG(x != out, "laneconv_fused: in-place is not possible (neighbour rows are read by other tiles)");
   if (!g_attr_set) {
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     g_attr_set = true;
   }
   PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
@@ -909,11 +923,12 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
   if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
   FusedArgs a;
+  memset(&a, 0, sizeof(a));
   a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.n_keys = n_keys; a.chain = chain; a.dbg = lgcn_debug_get();
   a.tl = g_timeline;
   const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  k_laneconv_fused<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  k_laneconv_fused<false><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   LGCN_LAUNCH_OK();
   return 0;
 }
