@@ -958,25 +958,56 @@ class Net(nn.Module):
             return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
 
 
-def prefetch_forward(net: "Net", batches):
+def prefetch_forward(net: "Net", batches, to_host: bool = False):
     """Generator over collated CPU batches -> outputs, with the host staging of batch i+1 (pack + H2D) overlapped
     with the device work of batch i: what a DataLoader with pinned prefetch gives the reference's training loop
     (train.py:118-143, ``pin_memory=True``).  Every batch still goes through ``Net.stage`` + ``Net.forward_device``,
     i.e. exactly ``Net.forward`` split at the H2D boundary.  (Staging on a worker thread instead was measured slower,
-    13.5 vs 10.1 ms per batch-128 step: the two threads contend for the GIL and the CUDA driver lock.)"""
+    13.5 vs 10.1 ms per batch-128 step: the two threads contend for the GIL and the CUDA driver lock.)
+
+    ``to_host=True`` yields the results as pinned CPU tensors (same dict of per-scene lists) and runs one batch
+    deeper: the D2H copy of batch i is queued on its own stream behind an event, batch i+1 is launched, and only then
+    is batch i handed out, so the device never waits for the host to read a result and relaunch."""
     it = iter(batches)
     try:
         staged = net.stage(next(it))
     except StopIteration:
         return
+    held = None   # (cls_host, reg_host, sizes, copied event) of the previous batch
     while staged is not None:
         out = net.forward_device(staged)          # enqueued; the host returns after the one pair-count sync
+        if to_host:
+            dev = out["cls"][0].device if out["cls"] else net._device()
+            with torch.cuda.device(dev):
+                cur, d2h = torch.cuda.current_stream(), _side_stream(dev, "d2h")
+                sizes = [len(x) for x in out["cls"]]
+                cls_d, reg_d = torch.cat(out["cls"]), torch.cat(out["reg"])
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done)
+                    cls_h = torch.empty(cls_d.shape, dtype=cls_d.dtype, pin_memory=True).copy_(cls_d, non_blocking=True)
+                    reg_h = torch.empty(reg_d.shape, dtype=reg_d.dtype, pin_memory=True).copy_(reg_d, non_blocking=True)
+                    cls_d.record_stream(d2h)
+                    reg_d.record_stream(d2h)
+                    copied = torch.cuda.Event()
+                    copied.record(d2h)
+            mine = (cls_h, reg_h, sizes, copied)
         try:
             nxt = net.stage(next(it))             # host packing + H2D of the next batch while the GPU computes
         except StopIteration:
             nxt = None
-        yield out
+        if not to_host:
+            yield out
+        else:
+            if held is not None:
+                held[3].synchronize()
+                yield {"cls": list(torch.split(held[0], held[2])), "reg": list(torch.split(held[1], held[2]))}
+            held = mine
         staged = nxt
+    if to_host and held is not None:
+        held[3].synchronize()
+        yield {"cls": list(torch.split(held[0], held[2])), "reg": list(torch.split(held[1], held[2]))}
 
 
 def get_model():

@@ -431,6 +431,13 @@ def test_prefetch_forward_equals_forward(cuda, lib, net):
             for a, b in zip(g[k], w[k]):
                 assert torch.equal(a, b)
     assert list(L.prefetch_forward(net, iter([]))) == []
+    host = list(L.prefetch_forward(net, iter(batches), to_host=True))   # one batch deeper, results on the host
+    assert len(host) == len(want)
+    for g, w in zip(host, want):
+        for k in ("cls", "reg"):
+            assert len(g[k]) == len(w[k])
+            for a, b in zip(g[k], w[k]):
+                assert not a.is_cuda and torch.equal(a, b.cpu())
 
 
 def test_net_forward_matches_oracle_batch8(cuda, lib, net):
