@@ -116,6 +116,7 @@ extern "C" int lgcn_linear128(const float* a0, const int32_t* idx0, const float*
   a.n_src = n_src; a.xs = xs; a.ks = ks; a.W = W; a.n_out_blocks = n_out_blocks;
   a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = ldo; a.m = m;
   a.dbg = g_debug;
+  a.w_hi = a.w_lo = nullptr;
   if (check_linear(a)) return -1;
   return lgcn_launch_linear(a, (cudaStream_t)stream);
 }
@@ -266,7 +267,8 @@ static AttW att_unpack(const float* p) {
 extern "C" int64_t lgcn_att_wpack_floats(void) { return 2 * LGCN_C + LGCN_C + 8 * CC + 10 * LGCN_C; }
 
 extern "C" int64_t lgcn_att_workspace_bytes(int64_t n_agt, int64_t n_pairs) {
-  return 3 * lgcn_align_up(n_pairs * LGCN_C * 4, 1024) + 2 * lgcn_align_up(n_agt * LGCN_C * 4, 1024) + 1024;
+  // 3 pair-row buffers | 2 agent-row buffers | the layer's 8 weight blocks split into tf32 hi / lo
+  return 3 * lgcn_align_up(n_pairs * LGCN_C * 4, 1024) + 2 * lgcn_align_up(n_agt * LGCN_C * 4, 1024) + 2 * 8 * CC * 4 + 1024;
 }
 
 extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs,
@@ -285,10 +287,32 @@ extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const flo
   float* A0 = (float*)((char*)workspace + 3 * pb);
   float* A1 = (float*)((char*)workspace + 3 * pb + ab);
   const int kLin = LGCN_EPI_GN | LGCN_EPI_RES | LGCN_EPI_RELU2;
+  // the six weight matrices of the layer as 8 tf32 hi / lo blocks, split by ONE launch (tcgen05 engine only):
+  // 0 dist.2 | 1 query | 2-4 ctx.0 (its three K=128 slices) | 5 ctx.1 | 6 agt | 7 linear
+  float* WH = (float*)((char*)workspace + 3 * pb + 2 * ab);
+  float* WL = WH + 8 * CC;
+  const bool pre = lgcn_get_gemm_engine() == 1;
+  if (pre) {
+    LgcnSplitList sl;
+    const float* ps[8] = {w.d2w, w.qw, w.c0w, w.c0w + LGCN_C, w.c0w + 2 * LGCN_C, w.c1w, w.aw, w.lw};
+    for (int b = 0; b < 8; ++b) {
+      sl.p[b] = ps[b];
+      sl.ldw[b] = (b >= 2 && b <= 4) ? 3 * LGCN_C : LGCN_C;
+    }
+    sl.n_blocks = 8;
+    if (int rc = lgcn_split_blocks_many(sl, WH, WL, st)) return rc;
+  }
+  auto with_w = [&](LinearArgs a, int blk) {
+    if (pre) {
+      a.w_hi = WH + (int64_t)blk * CC;
+      a.w_lo = WL + (int64_t)blk * CC;
+    }
+    return a;
+  };
   if (n_ctx == 0) {  // lanegcn.py:664-670 — no self.norm on this path
-    LinearArgs a = lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, LGCN_EPI_RELU1, A0, n_agt);
+    LinearArgs a = with_w(lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, LGCN_EPI_RELU1, A0, n_agt), 6);
     if (int rc = lgcn_launch_linear(a, st)) return rc;
-    LinearArgs l = lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt);
+    LinearArgs l = with_w(lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt), 7);
     return lgcn_launch_linear(l, st);
   }
   LGCN_CHECK_ARG(n_pairs > 0, "att_forward: no agent/context pair within the distance threshold in any scene "
@@ -296,33 +320,33 @@ extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const flo
   LGCN_CHECK_ARG(ctx && agt_ctrs && ctx_ctrs && hi && wi && rowptr, "att_forward: NULL argument");
   // dist = relu(GN(L(relu(L2(agt_ctrs[hi] - ctx_ctrs[wi])))))                      lanegcn.py:693-694
   if (int rc = lgcn_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, stream)) return rc;
-  LinearArgs d2 = lin1(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1, n_pairs);
+  LinearArgs d2 = with_w(lin1(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1, n_pairs), 0);
   if (int rc = lgcn_launch_linear(d2, st)) return rc;
   // query = relu(GN(L(agts[hi])))  — a per-row function: computed per agent when that is fewer rows   :696
   const float* q;
   const int32_t* qidx;
   if (n_agt <= n_pairs) {
-    LinearArgs qa = lin1(agts_in, nullptr, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, A0, n_agt);
+    LinearArgs qa = with_w(lin1(agts_in, nullptr, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, A0, n_agt), 1);
     if (int rc = lgcn_launch_linear(qa, st)) return rc;
     q = A0; qidx = hi;
   } else {
-    LinearArgs qp = lin1(agts_in, hi, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P2, n_pairs);
+    LinearArgs qp = with_w(lin1(agts_in, hi, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P2, n_pairs), 1);
     if (int rc = lgcn_launch_linear(qp, st)) return rc;
     q = P2; qidx = nullptr;
   }
   // ctx = L(relu(GN(L384(cat(dist, query, ctx[wi])))))  — split-K over the three sources, no cat   :698-700
-  LinearArgs c0 = lin1(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0, n_pairs);
+  LinearArgs c0 = with_w(lin1(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0, n_pairs), 2);
   c0.n_src = 3;
   c0.a[1] = q; c0.idx[1] = qidx;
   c0.a[2] = ctx; c0.idx[2] = wi;
   if (int rc = lgcn_launch_linear(c0, st)) return rc;
-  LinearArgs c1 = lin1(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1, n_pairs);
+  LinearArgs c1 = with_w(lin1(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1, n_pairs), 5);
   if (int rc = lgcn_launch_linear(c1, st)) return rc;
   // agts = relu(GN(agt(agts) + scatter(ctx by hi)))                                                  :702-705
-  LinearArgs ag = lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1, n_agt);
+  LinearArgs ag = with_w(lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1, n_agt), 6);
   if (int rc = lgcn_launch_linear(ag, st)) return rc;
   if (int rc = lgcn_segsum_gn_relu(A1, P1, rowptr, w.ng, w.nb, A0, n_agt, stream)) return rc;
   // agts = relu(GN(linear(agts)) + res)                                                              :707-709
-  LinearArgs l = lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt);
+  LinearArgs l = with_w(lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt), 7);
   return lgcn_launch_linear(l, st);
 }

@@ -94,6 +94,10 @@ struct LinearArgs {
   int64_t ldo;
   int64_t m;
   int dbg;  // ablation switches for profiling (lgcn_debug_flags); 0 in production
+  // optional: the weights already split into tf32 hi / lo blocks [n_src*128, 128] (lgcn_split_blocks_many); when
+  // NULL the tcgen05 path splits W into a scratch slot at launch
+  const float* w_hi;
+  const float* w_lo;
 };
 int lgcn_debug_get();
 int lgcn_launch_linear_simt(const LinearArgs& a, cudaStream_t st);
@@ -104,6 +108,13 @@ int lgcn_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_
 int lgcn_launch_wide_tc(const LinearArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st);
 int64_t lgcn_laneconv_fused_aux_bytes(int64_t n_edges);
 int lgcn_launch_linear_fused(const LinearArgs& a, cudaStream_t st);
+// split up to 8 weight blocks W_b[n, 0..127] = p[b][n * ldw[b] + 0..127] (n < 128) into hi / lo [n_blocks*128, 128]
+struct LgcnSplitList {
+  const float* p[8];
+  int64_t ldw[8];
+  int n_blocks;
+};
+int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st);
 int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, int64_t n_edges, int n_keys,
                                const float* w_hi, const float* w_lo, const float* gn, float* xa, int chain,
                                cudaStream_t st);

@@ -841,6 +841,20 @@ __global__ void k_split_blocks(const float* __restrict__ w, int64_t ldw, int n_s
   reinterpret_cast<float4*>(lo)[i] = b;
 }
 
+__global__ void k_split_many(const LgcnSplitList l, float* __restrict__ hi, float* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of the output
+  if (i >= l.n_blocks * 128 * 32) return;
+  const int c4 = i & 31, n = (i >> 5) & 127, b = i >> 12;
+  const float4 x = *reinterpret_cast<const float4*>(l.p[b] + (int64_t)n * l.ldw[b] + c4 * 4);
+  float4 a, c;
+  a.x = rna(x.x); c.x = rna(x.x - a.x);
+  a.y = rna(x.y); c.y = rna(x.y - a.y);
+  a.z = rna(x.z); c.z = rna(x.z - a.z);
+  a.w = rna(x.w); c.w = rna(x.w - a.w);
+  reinterpret_cast<float4*>(hi)[i] = a;
+  reinterpret_cast<float4*>(lo)[i] = c;
+}
+
 // Scratch for the split weights of a launch: a ring of device slots, each guarded by an event recorded after the
 // kernel that read it, so a slot is never rewritten (on any stream) before its last reader has finished.
 constexpr int kRing = 16;
@@ -851,6 +865,13 @@ bool g_ring_used[kRing];
 int g_ring_next = 0;
 }  // namespace
 
+int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st) {
+  LGCN_CHECK_ARG(l.n_blocks >= 1 && l.n_blocks <= 8, "split_blocks_many: n_blocks %d", l.n_blocks);
+  k_split_many<<<lgcn_cdiv(l.n_blocks * 128 * 32, 256), 256, 0, st>>>(l, hi, lo);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
 int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   if (la.m <= 0) return 0;
   LGCN_CHECK_ARG(la.n_out_blocks == 1 && la.ks == 0 && la.n_src >= 1 && la.n_src <= 3, "linear_fused: unsupported shape");
@@ -859,21 +880,27 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     g_attr_set = true;
   }
-  if (!g_ring) {
-    LGCN_CUDA_OK(cudaMalloc(&g_ring, kRing * kSlotFloats * sizeof(float)));
-    for (int i = 0; i < kRing; ++i) {
-      LGCN_CUDA_OK(cudaEventCreateWithFlags(&g_ring_ev[i], cudaEventDisableTiming));
-      g_ring_used[i] = false;
+  const float *w_hi = la.w_hi, *w_lo = la.w_lo;
+  int slot = -1;
+  if (!w_hi || !w_lo) {   // split W into a scratch slot
+    if (!g_ring) {
+      LGCN_CUDA_OK(cudaMalloc(&g_ring, kRing * kSlotFloats * sizeof(float)));
+      for (int i = 0; i < kRing; ++i) {
+        LGCN_CUDA_OK(cudaEventCreateWithFlags(&g_ring_ev[i], cudaEventDisableTiming));
+        g_ring_used[i] = false;
+      }
     }
+    slot = g_ring_next;
+    g_ring_next = (g_ring_next + 1) % kRing;
+    if (g_ring_used[slot]) LGCN_CUDA_OK(cudaStreamWaitEvent(st, g_ring_ev[slot], 0));
+    float* s_hi = g_ring + slot * kSlotFloats;
+    float* s_lo = s_hi + kSlotFloats / 2;
+    const int64_t ldw = (int64_t)la.n_src * LGCN_C + la.ks;
+    k_split_blocks<<<lgcn_cdiv(la.n_src * 128 * 32, 256), 256, 0, st>>>(la.W, ldw, la.n_src, s_hi, s_lo);
+    LGCN_LAUNCH_OK();
+    w_hi = s_hi;
+    w_lo = s_lo;
   }
-  const int slot = g_ring_next;
-  g_ring_next = (g_ring_next + 1) % kRing;
-  if (g_ring_used[slot]) LGCN_CUDA_OK(cudaStreamWaitEvent(st, g_ring_ev[slot], 0));
-  float* w_hi = g_ring + slot * kSlotFloats;
-  float* w_lo = w_hi + kSlotFloats / 2;
-  const int64_t ldw = (int64_t)la.n_src * LGCN_C + la.ks;
-  k_split_blocks<<<lgcn_cdiv(la.n_src * 128 * 32, 256), 256, 0, st>>>(la.W, ldw, la.n_src, w_hi, w_lo);
-  LGCN_LAUNCH_OK();
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, la.out, LGCN_C, la.m, la.ldo)) return rc;
   if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)la.n_src * LGCN_C, LGCN_C, 32, 128)) return rc;
@@ -893,8 +920,10 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
   k_laneconv_fused<true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   LGCN_LAUNCH_OK();
-  LGCN_CUDA_OK(cudaEventRecord(g_ring_ev[slot], st));
-  g_ring_used[slot] = true;
+  if (slot >= 0) {
+    LGCN_CUDA_OK(cudaEventRecord(g_ring_ev[slot], st));
+    g_ring_used[slot] = true;
+  }
   return 0;
 }
 
