@@ -191,7 +191,7 @@ int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int32_t* col, 
  * written to memory; ctr2 + GroupNorm + residual + ReLU run in the same kernel.  The plan is static per graph
  * (built from the merged CSR of lgcn_csr_build; n_edges = its entry count) and shared by every block and by
  * MapNet and M2M.  Same wpack, same result up to fp32 summation order.  tcgen05 engine only.
- * plan: lgcn_laneconv_plan_bytes; workspace: lgcn_laneconv_planned_workspace_bytes.                          */
+ * plan: lgcn_laneconv_plan_bytes; workspace: lgcn_laneconv_planned_workspace_bytes; n_blocks <= 8.           */
 int64_t lgcn_laneconv_plan_bytes(int64_t n_nodes, int64_t n_edges, int n_keys);
 int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes,
                              int64_t n_edges, void* plan, void* stream);

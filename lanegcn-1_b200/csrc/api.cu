@@ -197,10 +197,12 @@ extern "C" int lgcn_laneconv_stack(float* feat, const int32_t* rowptr, const int
 
 // Planned (aggregate-first) stack: every block is ONE kernel (laneconv_fused.cu); the features ping-pong between
 // `feat` and a workspace buffer because a block reads neighbour rows while other tiles already write theirs.
+// workspace: other feature buffer | aux rows | tf32 hi / lo copies of up to LGCN_MAX_PLANNED_BLOCKS blocks' wpack
+#define LGCN_MAX_PLANNED_BLOCKS 8
 extern "C" int64_t lgcn_laneconv_planned_workspace_bytes(int64_t n_nodes, int64_t n_edges, int n_keys) {
 #if LGCN_HAVE_TC
   return lgcn_align_up(n_nodes * LGCN_C * 4, 1024) + lgcn_laneconv_fused_aux_bytes(n_edges) +
-         2 * lgcn_align_up((int64_t)(n_keys + 2) * CC * 4, 1024) + 1024;
+         2 * lgcn_align_up(LGCN_MAX_PLANNED_BLOCKS * lgcn_laneconv_wpack_floats(n_keys) * 4, 1024) + 1024;
 #else
   (void)n_nodes; (void)n_edges; (void)n_keys;
   return 0;
@@ -211,23 +213,28 @@ extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_ed
                                            const float* wpack, int64_t n_nodes, void* workspace, void* stream) {
 #if LGCN_HAVE_TC
   LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "laneconv_stack_planned: n_keys %d", n_keys);
+  LGCN_CHECK_ARG(n_blocks >= 0 && n_blocks <= LGCN_MAX_PLANNED_BLOCKS, "laneconv_stack_planned: n_blocks %d", n_blocks);
   LGCN_CHECK_ARG(feat && plan && wpack && workspace, "laneconv_stack_planned: NULL argument");
   LGCN_CHECK_ARG(lgcn_get_gemm_engine() == 1, "laneconv_stack_planned needs the tcgen05 engine");
-  if (n_nodes <= 0) return 0;
+  if (n_nodes <= 0 || n_blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = n_keys + 1;
+  const int64_t per = lgcn_laneconv_wpack_floats(n_keys);
   float* other = (float*)workspace;
   float* xa = (float*)((char*)other + lgcn_align_up(n_nodes * LGCN_C * 4, 1024));
   float* w_hi = (float*)((char*)xa + lgcn_laneconv_fused_aux_bytes(n_edges));
-  float* w_lo = (float*)((char*)w_hi + lgcn_align_up((int64_t)(nb + 1) * CC * 4, 1024));
+  float* w_lo = (float*)((char*)w_hi + lgcn_align_up(LGCN_MAX_PLANNED_BLOCKS * per * 4, 1024));
+  // the whole pack (weights and, harmlessly, the norm vectors between them) is split by one launch
+  if (int rc = lgcn_split_tf32(wpack, w_hi, w_lo, (int64_t)n_blocks * per, st)) return rc;
   for (int i = 0; i < n_blocks; ++i) {
-    const float* w = wpack + (int64_t)i * lgcn_laneconv_wpack_floats(n_keys);   // Wcat | Wctr2 | 4 norm vectors
+    const float* w = wpack + (int64_t)i * per;   // Wcat | Wctr2 | 4 norm vectors
     const float* gn = w + (int64_t)(nb + 1) * CC;
     const float* src = (i & 1) ? other : feat;
     float* dst = (i & 1) ? feat : other;
-    if (int rc = lgcn_split_tf32(w, w_hi, w_lo, (int64_t)(nb + 1) * CC, st)) return rc;
     LgcnProfScope ps(LGCN_PROF_FUSED, st);
-    if (int rc = lgcn_launch_laneconv_fused(src, dst, plan, n_nodes, n_edges, n_keys, w_hi, w_lo, gn, xa, 1, st)) return rc;
+    if (int rc = lgcn_launch_laneconv_fused(src, dst, plan, n_nodes, n_edges, n_keys, w_hi + (int64_t)i * per,
+                                            w_lo + (int64_t)i * per, gn, xa, 1, st))
+      return rc;
   }
   if (n_blocks & 1) LGCN_CUDA_OK(cudaMemcpyAsync(feat, other, n_nodes * LGCN_C * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
