@@ -462,9 +462,9 @@ int num_sms() {
 
 int lgcn_launch_linear_tc(const LinearArgs& a, cudaStream_t st) {
   if (a.m <= 0) return 0;
-  // one output block, no rank-ks update: the aggregate-first kernel in linear mode (A operand through tensor memory,
+  // one output block: the aggregate-first kernel in linear mode (A operand through tensor memory,
   // TMA-fed pre-split weights) is 2-3x faster than k_linear_tc; debug flag 32768 keeps the old kernel
-  if (a.n_out_blocks == 1 && a.ks == 0 && !(a.dbg & 32768)) return lgcn_launch_linear_fused(a, st);
+  if (a.n_out_blocks == 1 && (a.ks == 0 || a.ks == 4) && !(a.dbg & 32768)) return lgcn_launch_linear_fused(a, st);
   LGCN_CHECK_ARG(a.n_src == 1 || a.n_out_blocks == 1, "linear128(tcgen05): several sources need n_out_blocks == 1");
   // (the LaneConv stack routes its 15-block projection to gemm_tc_wide.cu, which needs pre-split weights)
   if (!g_attr_set) {

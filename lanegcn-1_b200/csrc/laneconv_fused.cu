@@ -89,6 +89,9 @@ struct FusedArgs {
   const int32_t* idx[3];
   const float* res;
   const float* beta;     // linear mode: gn = gamma, beta separate
+  const float* xs;       // KS4: [M,4] extra input columns ...
+  const float* wx;       // ... and their weights: wx[n * ldw + j] = W[n, n_src*128 + j]
+  int64_t ldw;
   int flags;             // LGCN_EPI_* (linear mode)
   long long* tl;         // timeline buffer [1024][8] (dbg & 256, CTA 0 only)
   int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes, 128 no weight loads)
@@ -96,7 +99,8 @@ struct FusedArgs {
 
 // LINEAR = false: one LaneConv block (plan / table driven);  LINEAR = true: the generic Linear of lgcn_linear128.
 // Two instantiations so that neither hot loop carries the other mode's branches and registers.
-template <bool LINEAR>
+// KS4 (linear mode only): rank-4 update of the accumulators by four extra input columns (A2M.meta, lanegcn.py:387-395).
+template <bool LINEAR, bool KS4 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                  const __grid_constant__ CUtensorMap whi_map, const __grid_constant__ CUtensorMap wlo_map) {
@@ -156,6 +160,9 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const int32_t* __restrict__ idx1 = a.idx[1];
   const int32_t* __restrict__ idx2 = a.idx[2];
   const float* __restrict__ lin_res = a.res;
+  const float* __restrict__ lin_xs = a.xs;
+  const float* __restrict__ lin_wx = a.wx;
+  const int64_t lin_ldw = a.ldw;
   const int lin_flags = a.flags;
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
   const bool chain = a.chain != 0;
@@ -573,6 +580,17 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       drain(false);
 #pragma unroll
       for (int c = 0; c < 8; ++c) rb[c] = live ? __ldg(resp + 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (KS4) {   // the weights of the 4 extra columns are broadcast loads from L2
+        if (m < M) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(lin_xs + m * 4));
+          const float* wr = lin_wx + (int64_t)(h * 64) * lin_ldw;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wr + (int64_t)c * lin_ldw));
+            f[c] = fmaf(x.w, w.w, fmaf(x.z, w.z, fmaf(x.y, w.y, fmaf(x.x, w.x, f[c]))));
+          }
+        }
+      }
       if (lin_flags & LGCN_EPI_GN) gn(gam);
       if (lin_flags & LGCN_EPI_RELU1) {
 #pragma unroll
@@ -874,10 +892,12 @@ int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStr
 
 int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   if (la.m <= 0) return 0;
-  LGCN_CHECK_ARG(la.n_out_blocks == 1 && la.ks == 0 && la.n_src >= 1 && la.n_src <= 3, "linear_fused: unsupported shape");
+  LGCN_CHECK_ARG(la.n_out_blocks == 1 && (la.ks == 0 || la.ks == 4) && la.n_src >= 1 && la.n_src <= 3,
+                 "linear_fused: unsupported shape");
   if (!g_attr_set) {
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     g_attr_set = true;
   }
   const float *w_hi = la.w_hi, *w_lo = la.w_lo;
@@ -915,10 +935,16 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   a.gn = (la.flags & LGCN_EPI_GN) ? la.gamma : nullptr;
   a.beta = la.beta;
   a.res = la.res ? la.res : la.a[0];
+  if (la.ks == 4) {
+    a.xs = la.xs;
+    a.wx = la.W + (int64_t)la.n_src * LGCN_C;
+    a.ldw = (int64_t)la.n_src * LGCN_C + 4;
+  }
   a.flags = la.flags; a.M = la.m; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
   const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  k_laneconv_fused<true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  if (la.ks == 4) k_laneconv_fused<true, true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  else k_laneconv_fused<true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   LGCN_LAUNCH_OK();
   if (slot >= 0) {
     LGCN_CUDA_OK(cudaEventRecord(g_ring_ev[slot], st));
@@ -939,6 +965,7 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   if (!g_attr_set) {
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     g_attr_set = true;
   }
   PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
