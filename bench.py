@@ -254,16 +254,17 @@ def run_ours(args):
     # the device work of step i (lanegcn.prefetch_forward — a DataLoader-style prefetch).  Wall clock, max over
     # ranks.  The un-overlapped latency of one Net.forward(data) + D2H call is reported next to it.
     def finish(out):
-        if world > 1:
-            out = shard.gather_outputs(out, plan)
         if out["cls"] and not out["cls"][0].is_cuda:   # prefetch_forward(to_host=True): already pinned host tensors
             return out["cls"], out["reg"]
+        if world > 1:
+            out = shard.gather_outputs(out, plan)
         return [torch.cat(out["cls"]).cpu()], [torch.cat(out["reg"]).cpu()]
 
     def run_e2e(n):
         trace = os.environ.get("LGCN_E2E_TRACE") == "1"
         tt = [time.perf_counter()]
-        for out in L.prefetch_forward(net, (data for _ in range(n)), to_host=(world == 1)):
+        gather = (lambda o: shard.gather_outputs(o, plan)) if world > 1 else None
+        for out in L.prefetch_forward(net, (data for _ in range(n)), to_host=True, post=gather):
             res = finish(out)
             if trace:
                 tt.append(time.perf_counter())
@@ -401,8 +402,9 @@ def run_ours(args):
         "e2e": {"value": round(B / (e2e_ms / 1e3), 2), "unit": "scenes/s", "ms_per_step": round(e2e_ms, 4),
                 "single_call_latency_ms": round(lat_ms, 4), "stage_host_ms": round(stage_host_ms, 4),
                 "how": "Net.stage (pack into pinned memory + H2D) + Net.forward_device + D2H of cls/reg every step; "
-                       "staging of step i+1 overlapped with the device work of step i (prefetch_forward; at N=1 "
-                       "with to_host=True: D2H on its own stream, results handed out one batch later)",
+                       "staging of step i+1 overlapped with the device work of step i (prefetch_forward with "
+                       "to_host=True: result gather on the compute stream, D2H on its own stream, results handed "
+                       "out one batch later)",
                 "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(lt.item()),
         "roofline": roof,

@@ -958,7 +958,7 @@ class Net(nn.Module):
             return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
 
 
-def prefetch_forward(net: "Net", batches, to_host: bool = False):
+def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
     """Generator over collated CPU batches -> outputs, with the host staging of batch i+1 (pack + H2D) overlapped
     with the device work of batch i: what a DataLoader with pinned prefetch gives the reference's training loop
     (train.py:118-143, ``pin_memory=True``).  Every batch still goes through ``Net.stage`` + ``Net.forward_device``,
@@ -967,7 +967,9 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False):
 
     ``to_host=True`` yields the results as pinned CPU tensors (same dict of per-scene lists) and runs one batch
     deeper: the D2H copy of batch i is queued on its own stream behind an event, batch i+1 is launched, and only then
-    is batch i handed out, so the device never waits for the host to read a result and relaunch."""
+    is batch i handed out, so the device never waits for the host to read a result and relaunch.  ``post`` (optional)
+    maps the device outputs of a batch to the dict that is handed out / copied, on the compute stream right after the
+    forward (the multi-GPU result gather, ``shard.gather_outputs``)."""
     it = iter(batches)
     try:
         staged = net.stage(next(it))
@@ -976,6 +978,8 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False):
     held = None   # (cls_host, reg_host, sizes, copied event) of the previous batch
     while staged is not None:
         out = net.forward_device(staged)          # enqueued; the host returns after the one pair-count sync
+        if post is not None:
+            out = post(out)
         if to_host:
             dev = out["cls"][0].device if out["cls"] else net._device()
             with torch.cuda.device(dev):
