@@ -61,8 +61,10 @@ for name in ("tiny_b3", "argo_b1"):
     net = L.Net(L.config)
     net.load_state_dict(sd)
     net = net.to(dev).eval()
-    for eng in (0, 1):
+    net.use_cuda_graphs = False   # forward hooks copy to the host: not capturable
+    for eng, fused in ((0, False), (1, False), (1, True)):
         lib.lgcn_set_gemm_engine(eng)
+        L.LANECONV_FUSED = fused
         taps = {}
         hooks = [getattr(net, s).register_forward_hook(
             lambda m, i, o, s=s: taps.__setitem__(s, (o[0] if isinstance(o, tuple) else o).detach().cpu()))
@@ -71,7 +73,7 @@ for name in ("tiny_b3", "argo_b1"):
         for h in hooks:
             h.remove()
         taps["cls"], taps["reg"] = torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
-        print(f"--- {name} engine {eng}")
+        print(f"--- {name} engine {eng} ({'aggregate-first LaneConv' if fused else 'split LaneConv path'})")
         for s in ("actor_net", "map_net", "a2m", "m2m", "m2a", "a2a", "cls", "reg"):
             ref32, ref64, got = t32[s].double(), t64[s], taps[s].double()
             tol = 1e-5 + 1e-4 * ref32.abs()
