@@ -11,8 +11,24 @@ import torch.nn.functional as F
 from torch import nn
 
 
+class _GN1(nn.GroupNorm):
+    """GroupNorm with ONE group = LayerNorm over all non-batch dims with a per-channel affine.  On the GPU it is
+    spelled that way: ATen's GroupNorm path (RowwiseMoments + fused-params + elementwise kernels) was 0.8 ms of
+    ActorNet's 1.9 ms per batch-128 forward; the vectorised LayerNorm kernel does the same reduction in one launch.
+    Same parameters (``weight``, ``bias``), same state_dict keys."""
+
+    def forward(self, x):
+        if not x.is_cuda:
+            return super().forward(x)
+        if x.dim() == 2:
+            return F.layer_norm(x, x.shape[1:], self.weight, self.bias, self.eps)
+        y = F.layer_norm(x, x.shape[1:], None, None, self.eps)
+        shape = (1, -1) + (1,) * (x.dim() - 2)
+        return torch.addcmul(self.bias.view(shape), y, self.weight.view(shape))
+
+
 def _gn(c: int) -> nn.GroupNorm:
-    return nn.GroupNorm(1, c)
+    return _GN1(1, c)
 
 
 class Linear(nn.Module):
