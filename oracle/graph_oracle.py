@@ -69,6 +69,20 @@ def merged_csr(edges, n, n_keys=None):
     return np.cumsum(rowptr).astype(np.int32), blk[order].astype(np.int32)
 
 
+def laneconv_plan(edges, n, tile=128):
+    """What lgcn_laneconv_plan_build must encode for the aggregate-first LaneConv kernel: for every destination row m
+    and key k the ordered list of source rows (edge-list order) — exactly the terms ``temp.index_add_(0, u, W_k x[v])``
+    adds into row m (lanegcn.py:333-354).  Returns ``lists[k][m]`` (python lists) and the padded row count."""
+    rows = (n + tile - 1) // tile * tile
+    lists = []
+    for u, v in edges:
+        per = [[] for _ in range(n)]
+        for uu, vv in zip(np.asarray(u, np.int64).tolist(), np.asarray(v, np.int64).tolist()):
+            per[uu].append(vv)
+        lists.append(per)
+    return lists, rows
+
+
 def pair_list(agt_ctrs, ctx_ctrs, dist_th, fix_empty_scene_offsets=False):
     """hi,wi int64 for lists of per-scene f32[*,2] centres (lanegcn.py:672-689).  fp32 arithmetic with
     separate roundings: sub, square, add, sqrt, <=."""

@@ -280,6 +280,45 @@ def test_gather_gn_relu_matches_index_add_order(cuda, lib):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("name", ["tiny_b3", "argo_b1"])
+def test_laneconv_plan_matches_oracle(cuda, lib, name):
+    """The gather plan of the aggregate-first kernel, decoded, is EXACTLY the per-(row, key) source lists of the
+    reference's index_add_ loop (integer structure: bit-exact, order included); padding rows have no sources."""
+    batch = synth.collate(golden_scenes(name))
+    og = O.graph_gather(O.to_long(batch["graph"]))
+    edges = graph_oracle.edge_lists(og)
+    n, K = og["feats"].shape[0], len(edges)
+    want, rows = graph_oracle.laneconv_plan(edges, n)
+    pg = L.graph_gather(batch["graph"])["_packed"]
+    plan = pg.plan()
+    torch.cuda.synchronize()
+    raw = plan.cpu().numpy()
+    hdr = raw[:256].view(np.int32)
+    n_multi, n_mcol = int(hdr[0]), int(hdr[1])
+    n_tiles = rows // 128
+    off = 256
+    tab = raw[off:off + n_tiles * K * 128 * 4].view(np.int32).reshape(n_tiles, K, 128)
+    off += (n_tiles * K * 128 * 4 + 255) // 256 * 256
+    max_multi = pg.n_edges // 2
+    mdesc = raw[off:off + (max_multi + 1) * 8].view(np.int32).reshape(-1, 2)
+    off += ((max_multi + 1) * 8 + 255) // 256 * 256
+    mcol = raw[off:off + pg.n_edges * 4].view(np.int32)
+    assert n_multi == sum(1 for k in range(K) for m in range(n) if len(want[k][m]) > 1)
+    assert n_mcol == sum(len(want[k][m]) for k in range(K) for m in range(n) if len(want[k][m]) > 1)
+    for k in range(K):
+        for m in range(rows):
+            v = int(tab[m // 128, k, m % 128])
+            exp = want[k][m] if m < n else []
+            if v == -1:
+                got = []
+            elif v >= 0:
+                got = [v]
+            else:
+                s0, c = mdesc[-2 - v]
+                got = mcol[s0:s0 + c].tolist()
+            assert got == exp, f"key {k} row {m}: {got} vs {exp}"
+
+
 @pytest.mark.parametrize("n,n_keys,n_blocks,seed", [(1, 14, 1, 0), (127, 14, 2, 1), (129, 3, 3, 2), (1000, 14, 4, 3),
                                                      (4097, 14, 4, 4), (300, 0, 2, 5), (20000, 14, 1, 6)])
 def test_laneconv_stack_planned_matches_split_fp32(cuda, lib, n, n_keys, n_blocks, seed):

@@ -105,6 +105,25 @@ def test_merged_csr_is_stable_by_destination():
         assert col[rowptr[r]:rowptr[r + 1]].tolist() == want
 
 
+def test_laneconv_plan_oracle_agrees_with_merged_csr():
+    """Two restatements of the same index_add_ order: the merged CSR (split LaneConv path) and the per-(row, key)
+    source lists (aggregate-first path) must describe the same terms in the same order."""
+    batch = synth.collate(golden_scenes("tiny_b3"))
+    graph = O.graph_gather(O.to_long(batch["graph"]))
+    edges = graph_oracle.edge_lists(graph)
+    n, K = graph["feats"].shape[0], len(edges)
+    rowptr, col = graph_oracle.merged_csr(edges, n)
+    lists, rows = graph_oracle.laneconv_plan(edges, n)
+    assert rows % 128 == 0 and rows >= n and len(lists) == K
+    multi = 0
+    for m in range(n):
+        want = [(int(c) % (K + 1) - 1, int(c) // (K + 1)) for c in col[rowptr[m]:rowptr[m + 1]]]
+        got = [(k, v) for k in range(K) for v in lists[k][m]]
+        assert got == want
+        multi += sum(len(lists[k][m]) > 1 for k in range(K))
+    assert multi > 0, "fixture should contain multi-source (row, key) pairs"
+
+
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
 def test_oracle_is_bit_identical_to_reference():
     ref_lanegcn, ref_data = ref_loader.load()
