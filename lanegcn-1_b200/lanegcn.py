@@ -44,16 +44,58 @@ LANECONV_FUSED = os.environ.get("LGCN_LANECONV", "fused") != "split"
 # --------------------------------------------------------------------------- small host-side helpers
 class SceneList(list):
     """A list of per-scene tensors (what the reference passes around as ``*_idcs`` / ``*_ctrs``) that also
-    remembers the batched tensor it was split from and the scene offsets, so nothing is re-concatenated."""
+    remembers the batched tensor it was split from and the scene offsets, so nothing is re-concatenated.
+
+    The per-scene views can be created lazily (``scene_list(..., lazy=True)``): splitting a batch into 128 views costs
+    ~0.2 ms of host time, the forward itself only ever uses ``cat`` / ``off_dev`` / ``sizes``, and five such lists per
+    forward were ~1 ms of launch delay.  Every Python-level access fills the list first; lists handed out through
+    the public functions (``graph_gather``, ``actor_gather``) are filled eagerly because C-level consumers such as
+    ``torch.cat(lst)`` read the underlying list storage directly."""
 
     cat: Optional[Tensor] = None       # the batched tensor the entries are views of
     off: Optional[List[int]] = None    # python offsets, len B+1
     off_dev: Optional[Tensor] = None   # int32 [B+1] on the device
+    sizes: Optional[List[int]] = None  # rows per scene
+    _lazy: bool = False
+
+    def materialize(self) -> "SceneList":
+        if self._lazy:
+            self._lazy = False
+            list.extend(self, self.cat.split_with_sizes(self.sizes))
+        return self
+
+    def __len__(self):
+        return len(self.sizes) if self._lazy else list.__len__(self)
+
+    def __iter__(self):
+        return list.__iter__(self.materialize())
+
+    def __getitem__(self, i):
+        return list.__getitem__(self.materialize(), i)
+
+    def __repr__(self):
+        return list.__repr__(self.materialize())
+
+    def __eq__(self, other):
+        return list.__eq__(self.materialize(), other)
+
+    __hash__ = None
+
+    def __add__(self, other):
+        return list.__add__(self.materialize(), other)
+
+    def __reversed__(self):
+        return list.__reversed__(self.materialize())
+
+    def __contains__(self, x):
+        return list.__contains__(self.materialize(), x)
 
 
-def scene_list(cat: Tensor, sizes: List[int], off_dev: Optional[Tensor] = None) -> SceneList:
-    out = SceneList(torch.split(cat, sizes))
+def scene_list(cat: Tensor, sizes: List[int], off_dev: Optional[Tensor] = None, lazy: bool = False) -> SceneList:
+    out = SceneList()
     out.cat = cat
+    out.sizes = list(sizes)
+    out._lazy = True
     off = [0]
     for s in sizes:
         off.append(off[-1] + s)
@@ -62,7 +104,7 @@ def scene_list(cat: Tensor, sizes: List[int], off_dev: Optional[Tensor] = None) 
         off_t = torch.tensor(off, dtype=torch.int32)
         off_dev = _stage(off_t, cat.device, torch.int32, "scene_off") if cat.is_cuda else off_t
     out.off_dev = off_dev
-    return out
+    return out if lazy else out.materialize()
 
 
 def _as_scene_list(lst, sizes: Optional[List[int]] = None) -> SceneList:
@@ -347,7 +389,7 @@ def stage_graphs(graphs: List[dict], extra_float: Optional[List[Tensor]] = None,
     return sg
 
 
-def finish_graph(sg: StagedGraphs) -> dict:
+def finish_graph(sg: StagedGraphs, lazy: bool = False) -> dict:
     """Device side of graph_gather: widen + offset the indices, assemble the reference's dict (views of
     the arenas, no copies) and build the destination-sorted CSR."""
     lib = _C.lib()
@@ -361,8 +403,8 @@ def finish_graph(sg: StagedGraphs) -> dict:
                                      sg.segs[n_seg + 1:].data_ptr(), n_seg, total, e64.data_ptr(),
                                      _C.stream_ptr()), "offset_indices")
     graph = dict()
-    graph["idcs"] = scene_list(torch.arange(N, device=dev), sizes, sg.off_dev)
-    graph["ctrs"] = scene_list(ctrs, sizes, sg.off_dev)
+    graph["idcs"] = scene_list(torch.arange(N, device=dev), sizes, sg.off_dev, lazy=lazy)
+    graph["ctrs"] = scene_list(ctrs, sizes, sg.off_dev, lazy=lazy)
     graph["feats"], graph["turn"], graph["control"], graph["intersect"] = feats, turn, control, intersect
     S = sg.num_scales
     graph["pre"], graph["suc"] = [dict() for _ in range(S)], [dict() for _ in range(S)]
@@ -894,7 +936,7 @@ class Net(nn.Module):
                 b.rot = fl[62 * A: 62 * A + 4 * B].view(B, 2, 2)
                 b.orig = fl[62 * A + 4 * B: 62 * A + 6 * B].view(B, 2)
                 cnt, off_dev = sg.extra_i64, sg.extra_i32
-            b.actor_ctrs = scene_list(ctrs, sizes, off_dev)
+            b.actor_ctrs = scene_list(ctrs, sizes, off_dev, lazy=True)
             b.rot_a = torch.repeat_interleave(b.rot, cnt, 0, output_size=A)     # the scene's rot / orig per actor
             b.orig_a = torch.repeat_interleave(b.orig, cnt, 0, output_size=A)
             b.graphs = sg
@@ -905,7 +947,8 @@ class Net(nn.Module):
 
     @torch.no_grad()
     def forward(self, data: Dict) -> Dict[str, List[Tensor]]:
-        return self.forward_device(self.stage(data))
+        out = self.forward_device(self.stage(data))
+        return {k: v.materialize() if isinstance(v, SceneList) else v for k, v in out.items()}
 
     @torch.no_grad()
     def forward_device(self, b: DeviceBatch) -> Dict[str, List[Tensor]]:
@@ -926,9 +969,10 @@ class Net(nn.Module):
                 x = b.actors.transpose(1, 2).contiguous()
                 actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
             actor_ctrs = b.actor_ctrs
-            sizes = [len(x) for x in actor_ctrs]
-            actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev)
-            graph = finish_graph(b.graphs)                                        # lanegcn.py:134
+            sizes = actor_ctrs.sizes
+            actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev,
+                                    lazy=True)
+            graph = finish_graph(b.graphs, lazy=True)                             # lanegcn.py:134
             node_ctrs = graph["ctrs"]
             # the three pair lists depend on centres only: count them up front ...
             pls = count_pair_lists([
@@ -955,7 +999,17 @@ class Net(nn.Module):
                 cls, reg = cls.clone(), reg.clone()  # graph outputs are static buffers reused by the next replay
             else:
                 cls, reg = self._pred_core(actors, actor_ctrs.cat, b.rot_a, b.orig_a)
-            return {"cls": list(torch.split(cls, sizes)), "reg": list(torch.split(reg, sizes))}
+            # per-scene lists like the reference's; the views are created on first access (Net.forward fills them
+            # before returning, the throughput paths read ``.cat``)
+            return {"cls": scene_list(cls, sizes, actor_ctrs.off_dev, lazy=True),
+                    "reg": scene_list(reg, sizes, actor_ctrs.off_dev, lazy=True)}
+
+
+def _cat_of(lst) -> Tensor:
+    """The batched tensor behind a per-scene list (no concatenation when it is a SceneList)."""
+    if isinstance(lst, SceneList) and lst.cat is not None:
+        return lst.cat
+    return torch.cat(list(lst), 0)
 
 
 def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
@@ -984,8 +1038,8 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
             dev = out["cls"][0].device if out["cls"] else net._device()
             with torch.cuda.device(dev):
                 cur, d2h = torch.cuda.current_stream(), _side_stream(dev, "d2h")
-                sizes = [len(x) for x in out["cls"]]
-                cls_d, reg_d = torch.cat(out["cls"]), torch.cat(out["reg"])
+                sizes = out["cls"].sizes if isinstance(out["cls"], SceneList) else [len(x) for x in out["cls"]]
+                cls_d, reg_d = _cat_of(out["cls"]), _cat_of(out["reg"])
                 done = torch.cuda.Event()
                 done.record(cur)
                 with torch.cuda.stream(d2h):
@@ -1002,16 +1056,16 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
         except StopIteration:
             nxt = None
         if not to_host:
-            yield out
+            yield {k: v.materialize() if isinstance(v, SceneList) else v for k, v in out.items()}
         else:
             if held is not None:
                 held[3].synchronize()
-                yield {"cls": list(torch.split(held[0], held[2])), "reg": list(torch.split(held[1], held[2]))}
+                yield {"cls": list(held[0].split_with_sizes(held[2])), "reg": list(held[1].split_with_sizes(held[2]))}
             held = mine
         staged = nxt
     if to_host and held is not None:
         held[3].synchronize()
-        yield {"cls": list(torch.split(held[0], held[2])), "reg": list(torch.split(held[1], held[2]))}
+        yield {"cls": list(held[0].split_with_sizes(held[2])), "reg": list(held[1].split_with_sizes(held[2]))}
 
 
 def get_model():

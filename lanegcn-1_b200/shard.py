@@ -59,11 +59,12 @@ def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, 
     reg [A,K,T,2] are packed side by side into a [max_actors, K + K*T*2] buffer (1,464 B per actor in the
     reference config) and all_gathered; no host synchronisation when ``plan`` is given."""
     if plan is None:
-        plan = make_plan([len(x) for x in out["cls"]], group)
+        plan = make_plan(list(out["cls"].sizes) if getattr(out["cls"], "sizes", None) is not None else [len(x) for x in out["cls"]], group)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     mine = plan.per_rank[rank]
-    if out["cls"]:
-        cls, reg = torch.cat(out["cls"], 0), torch.cat(out["reg"], 0)
+    if len(out["cls"]):
+        cat_of = lambda l: l.cat if getattr(l, "cat", None) is not None else torch.cat(list(l), 0)  # noqa: E731
+        cls, reg = cat_of(out["cls"]), cat_of(out["reg"])
         k, tail = cls.shape[1], tuple(reg.shape[1:])
         dev = cls.device
     else:  # a rank without scenes still takes part; shapes follow the reference config

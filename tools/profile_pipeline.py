@@ -22,7 +22,7 @@ for i in range(8):
     t2 = time.perf_counter()
     torch.cuda.synchronize()
     t3 = time.perf_counter()
-    c, r = torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
+    c, r = L._cat_of(out["cls"]).cpu(), L._cat_of(out["reg"]).cpu()
     t4 = time.perf_counter()
     T.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
 for row in T:
@@ -37,7 +37,7 @@ torch.cuda.synchronize()
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(12); print(s.getvalue()[:3000])
 
 def finish(out):
-    return torch.cat(out["cls"]).cpu(), torch.cat(out["reg"]).cpu()
+    return L._cat_of(out["cls"]).cpu(), L._cat_of(out["reg"]).cpu()
 
 def run_e2e(n):
     for out in L.prefetch_forward(net, (data for _ in range(n))):
