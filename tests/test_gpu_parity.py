@@ -479,6 +479,29 @@ def test_prefetch_forward_equals_forward(cuda, lib, net):
                 assert not a.is_cuda and torch.equal(a, b.cpu())
 
 
+def test_weight_updates_are_seen(cuda, lib):
+    """The packed weight copies follow in-place updates, load_state_dict and re-assigned Parameter objects."""
+    n1 = L.Net(L.config)
+    n1.load_state_dict(weights())
+    n1 = n1.to(cuda).eval()
+    batch = synth.collate(golden_scenes("tiny_b3"))
+    a = torch.cat(n1(batch)["reg"])
+    with torch.no_grad():
+        n1.m2m.fuse["ctr"][0].weight.mul_(1.25)
+        n1.a2a.att[1].agt.weight.add_(0.01)
+    b = torch.cat(n1(batch)["reg"])
+    assert not torch.equal(a, b)
+    n2 = L.Net(L.config)
+    n2.load_state_dict({k: v.clone() for k, v in n1.state_dict().items()})
+    n2 = n2.to(cuda).eval()
+    assert torch.equal(torch.cat(n2(batch)["reg"]), b)
+    n1.load_state_dict(weights())
+    assert torch.equal(torch.cat(n1(batch)["reg"]), a)
+    q = n1.m2a.att[0].query.linear
+    q.weight = torch.nn.Parameter(q.weight.detach() * 0.5)   # a new Parameter object under the same name
+    assert not torch.equal(torch.cat(n1(batch)["reg"]), a)
+
+
 def test_net_forward_matches_oracle_batch8(cuda, lib, net):
     scenes = synth.make_scenes(8, "small", seed0=20)
     sd = weights()
