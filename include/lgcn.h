@@ -39,10 +39,15 @@ const char* lgcn_last_error(void);
 int lgcn_get_gemm_engine(void);
 int lgcn_set_gemm_engine(int engine);
 
-/* Profiling ablations of the tcgen05 GEMM (results become WRONG; never set in production; returns the previous
- * value): 1 = epilogue skips staging + TMA stores, 2 = epilogue skips the cross-accumulator reads,
- * 4 = MMA issuer skips the tcgen05.mma instructions, 8 = producers skip global loads and conversion,
- * 16 = route the multi-block projection through the generic kernel instead of the A-in-TMEM one (results stay right). */
+/* Profiling ablations of the tcgen05 kernels (results become WRONG unless noted; never set in production; returns
+ * the previous value): 1 = epilogue skips staging + TMA stores, 2 = epilogue skips the cross-accumulator reads
+ * (gemm_tc*.cu), 4 = MMA issuer skips the tcgen05.mma instructions, 8 = producers skip global loads (and, in
+ * gemm_tc*.cu, the conversion), 16 = route the multi-block projection through the generic kernel instead of the
+ * A-in-TMEM one (results stay right); aggregate-first kernel only: 32 = no A conversion / tcgen05.st,
+ * 64 = no accumulator flushes, 128 = no weight TMA, 256 = write the clock timeline (needs a -DLGCN_TIMELINE build,
+ * lgcn_debug_timeline), 512 = flush every 5 keys instead of 3 (results stay within tolerance on the goldens but
+ * not on the stress case of tools/precision_fused.py); 32768 = one-block Linears on the first-generation k_linear_tc
+ * instead of the linear mode of the aggregate-first kernel (results stay right). */
 int lgcn_debug_flags(int flags);
 /* Profiling aid: device buffer [1024][8] of int64 clock stamps filled by CTA 0 of the aggregate-first LaneConv kernel
  * while debug flag 256 is set (tools/timeline_fused.py). */
