@@ -58,6 +58,12 @@ def cpu_forward_rate(steps: int, warmup: int, n_scenes: int = CPU_SAMPLE_SCENES)
     from lanegcn_b200 import synth
     from oracle import lanegcn_oracle as O
 
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        n_thr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_thr = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_thr))
     shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_shapes.json")))
     sd = synth.seeded_state_dict(shapes, 0)
     data = synth.collate(synth.make_scenes(n_scenes, PRESET, seed0=0))
