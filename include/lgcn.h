@@ -82,6 +82,10 @@ int lgcn_offset_indices(const void* local, int idx_bytes, const int64_t* seg_sta
 int lgcn_pack_meta(const float* turn, const float* control, const float* intersect, float* meta, int64_t n,
                    void* stream);
 
+/* actor_gather (lanegcn.py:155-168): out[a, c, t] = feats[a, t, c] for the concatenated actor histories
+ * ([n_actors, n_steps = 20, n_channels = 3] -> [n_actors, 3, 20], the channels-first layout ActorNet reads).      */
+int lgcn_actor_gather(const float* feats, float* out, int64_t n_actors, int n_steps, int n_channels, void* stream);
+
 /* Destination-sorted merged CSR of the K edge sets of one LaneConv block (accumulation order of
  * lanegcn.py:333-354: key order as given, then edge-list order — a STABLE sort by destination u).
  *   h_u[k], h_v[k] : device pointers to int64 u_k (destination) / v_k (source), h_len[k] their lengths
@@ -217,6 +221,91 @@ int lgcn_att_forward(const float* agts_in, float* agts_out, const float* ctx, co
                      const float* ctx_ctrs, const int32_t* hi, const int32_t* wi, const int32_t* rowptr,
                      int64_t n_agt, int64_t n_ctx, int64_t n_pairs, const float* wpack, void* workspace,
                      void* stream);
+
+/* ------------------------------------------------------------------ the whole forward graph path in ONE call
+ * graph_gather (utils.to_long + lanegcn.py:171-209) -> CSR + gather plan -> the three Att pair lists (:672-689) ->
+ * MapNet (:311-363) -> A2M (:385-407) -> M2M (:445-480) -> M2A (:502-513) -> A2A (:534-545), i.e. lanegcn.py:134-141
+ * of Net.forward, enqueued on `stream` with NO host synchronisation and no data-dependent host decision: every row
+ * count that depends on the batch (nodes, actors, pairs) is read from DEVICE memory, the buffers are sized by the
+ * capacities below, and the call is therefore capturable in a CUDA graph that is replayed for any batch that fits the
+ * capacities.  tcgen05 engine only.
+ *
+ *   dims        device int32[4]: {n_nodes, n_actors, 0, 0} of this batch (<= cap_nodes / cap_actors)
+ *   node_off / actor_off   device int32[cap_scenes + 1]: row offsets per scene, PADDED with the totals
+ *   local_idx   scene-local edge indices (idx_bytes = 2/4/8), segments back to back in output order
+ *               (key: pre0,suc0,...,left,right; then u|v; then scene slot 0..cap_scenes-1);
+ *   segs        device int64[2 S + 1], S = 2 * (2 n_scales + 2) * cap_scenes: seg_start[S + 1] | seg_add[S]
+ *               (lgcn_offset_indices); slots of absent scenes are empty segments
+ *   nodes       [cap_nodes,128] in/out: MapNet writes it, A2M / M2M update it
+ *   actors      [cap_actors,128] in/out: ActorNet's output on entry, M2A / A2A update it
+ *   stages      bit mask of LGCN_STAGE_* (a tap after any stage = run the mask in pieces)
+ *   status      device int32[8], zeroed by the GRAPH stage: [0] flag bits LGCN_ST_*, [1..3] exact pair counts of
+ *               A2M / M2A / A2A, [4] != 0 if an edge index was out of range.  The caller reads it when it next
+ *               synchronises: an overflow means the pair capacity was too small (results invalid: rerun larger).
+ *   w           the module weights (fp32, state_dict layouts named below) + `prepared`: their tf32 hi / lo images
+ *               written by lgcn_forward_prepare (once per weight version; lgcn_forward_prepared_bytes).           */
+#define LGCN_STAGE_GRAPH 1
+#define LGCN_STAGE_MAPNET 2
+#define LGCN_STAGE_A2M 4
+#define LGCN_STAGE_M2M 8
+#define LGCN_STAGE_M2A 16
+#define LGCN_STAGE_A2A 32
+#define LGCN_STAGE_ALL 63
+#define LGCN_ST_OVERFLOW_A2M 1
+#define LGCN_ST_OVERFLOW_M2A 2
+#define LGCN_ST_OVERFLOW_A2A 4
+#define LGCN_ST_EMPTY_A2M 8
+#define LGCN_ST_EMPTY_M2A 16
+#define LGCN_ST_EMPTY_A2A 32
+
+typedef struct LgcnForwardWeights {
+  const float* map_input;   /* input.0.weight[128,2] | input.0.bias[128] | input.2.linear.weight[128,128] | input.2.norm.{weight,bias} */
+  const float* map_seg;     /* same layout for MapNet.seg                                                              */
+  const float* map_fuse;    /* 4 blocks of the LaneConv wpack (lgcn_laneconv_wpack_floats)                             */
+  const float* a2m_meta;    /* meta.linear.weight[128,132] | meta.norm.weight[128] | meta.norm.bias[128]               */
+  const float* att[6];      /* Att wpack (lgcn_att_wpack_floats): a2m.att.0, a2m.att.1, m2a.att.0/1, a2a.att.0/1       */
+  const float* m2m_fuse;    /* 4 blocks of the LaneConv wpack                                                          */
+  void* prepared;           /* lgcn_forward_prepared_bytes(n_scales) bytes, written by lgcn_forward_prepare            */
+} LgcnForwardWeights;
+
+typedef struct LgcnForwardArgs {
+  int64_t cap_nodes, cap_actors, cap_index;   /* cap_index: capacity of local_idx in entries (2 per edge)          */
+  int64_t cap_pairs[3];                       /* A2M, M2A, A2A                                                     */
+  int32_t cap_scenes, n_scales, idx_bytes, keep_pair_quirk;
+  float dist_th[3];                           /* actor2map_dist, map2actor_dist, actor2actor_dist                  */
+  int32_t stages;
+  const int32_t* dims;
+  const int32_t* node_off;
+  const int32_t* actor_off;
+  const float* node_ctrs;                     /* [n_nodes,2]                                                       */
+  const float* node_feats;                    /* [n_nodes,2]                                                       */
+  const float* turn;                          /* [n_nodes,2]                                                       */
+  const float* control;                       /* [n_nodes]                                                         */
+  const float* intersect;                     /* [n_nodes]                                                         */
+  const float* actor_ctrs;                    /* [n_actors,2]                                                      */
+  const void* local_idx;
+  const int64_t* segs;
+  float* nodes;
+  float* actors;
+  int32_t* status;
+  LgcnForwardWeights w;
+  void* workspace;                            /* lgcn_forward_workspace_bytes(&args)                               */
+} LgcnForwardArgs;
+
+/* World transform of the predictions (lanegcn.py:145-150): reg[a, :, :, :] <- reg[a] . rot[b] + orig[b] with b the
+ * scene of actor a (actor_off int32[n_scenes + 1], padded with the total), in place; reg holds points_per_actor
+ * (= num_mods x num_preds) float2 per actor.  n_actors_dev (may be NULL): live actor count in device memory.      */
+int lgcn_world_transform(float* reg, const int32_t* actor_off, int n_scenes, const float* rot, const float* orig,
+                         int64_t n_actors, const int32_t* n_actors_dev, int points_per_actor, void* stream);
+
+int64_t lgcn_forward_prepared_bytes(int n_scales);
+int lgcn_forward_prepare(const LgcnForwardWeights* w, int n_scales, void* stream);
+int64_t lgcn_forward_workspace_bytes(const LgcnForwardArgs* args);
+int lgcn_forward(const LgcnForwardArgs* args, void* stream);
+/* Device pointers into the workspace for parity tests of the index side (valid after the GRAPH stage): which = 0 CSR
+ * rowptr int32[n+1], 1 CSR col int32[E], 2 batched int64 u|v arena (e64), 3/4/5 hi int32[P] of A2M / M2A / A2A,
+ * 6/7/8 wi int32[P], 9/10/11 destination rowptr of the three lists.  Returns NULL for an unknown selector.       */
+void* lgcn_forward_buffer(const LgcnForwardArgs* args, int which);
 
 #ifdef __cplusplus
 }

@@ -58,8 +58,36 @@ _SIGS = {
     "lgcn_laneconv_stack_planned": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
     "lgcn_att_wpack_floats": (_i64, []),
     "lgcn_att_workspace_bytes": (_i64, [_i64, _i64]),
+    "lgcn_actor_gather": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "lgcn_world_transform": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "lgcn_forward_prepared_bytes": (_i64, [_i32]),
+    "lgcn_forward_prepare": (_i32, [_vp, _i32, _vp]),
+    "lgcn_forward_workspace_bytes": (_i64, [_vp]),
+    "lgcn_forward": (_i32, [_vp, _vp]),
+    "lgcn_forward_buffer": (_vp, [_vp, _i32]),
     "lgcn_att_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
 }
+
+
+
+class ForwardWeights(C.Structure):
+    """LgcnForwardWeights (include/lgcn.h)."""
+    _fields_ = [("map_input", _vp), ("map_seg", _vp), ("map_fuse", _vp), ("a2m_meta", _vp), ("att", _vp * 6),
+                ("m2m_fuse", _vp), ("prepared", _vp)]
+
+
+class ForwardArgs(C.Structure):
+    """LgcnForwardArgs (include/lgcn.h)."""
+    _fields_ = [("cap_nodes", _i64), ("cap_actors", _i64), ("cap_index", _i64), ("cap_pairs", _i64 * 3),
+                ("cap_scenes", C.c_int32), ("n_scales", C.c_int32), ("idx_bytes", C.c_int32),
+                ("keep_pair_quirk", C.c_int32), ("dist_th", _f32 * 3), ("stages", C.c_int32),
+                ("dims", _vp), ("node_off", _vp), ("actor_off", _vp), ("node_ctrs", _vp), ("node_feats", _vp),
+                ("turn", _vp), ("control", _vp), ("intersect", _vp), ("actor_ctrs", _vp), ("local_idx", _vp),
+                ("segs", _vp), ("nodes", _vp), ("actors", _vp), ("status", _vp), ("w", ForwardWeights),
+                ("workspace", _vp)]
+
+
+STAGE_GRAPH, STAGE_MAPNET, STAGE_A2M, STAGE_M2M, STAGE_M2A, STAGE_A2A, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
 
 _lib = None
 

@@ -21,6 +21,8 @@ static size_t g_prof_used = 0;
 static bool g_prof_on = false;
 LgcnProfScope::LgcnProfScope(int kind, cudaStream_t s) : slot(-1), st(s) {
   if (!g_prof_on) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;  // timing is for eager runs
   if (g_prof_used == g_prof_pool.size()) {
     ProfEv e;
     if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
@@ -117,18 +119,23 @@ extern "C" int lgcn_linear128(const float* a0, const int32_t* idx0, const float*
   a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = ldo; a.m = m;
   a.dbg = g_debug;
   a.w_hi = a.w_lo = nullptr;
+  a.m_dev = nullptr;
   if (check_linear(a)) return -1;
   return lgcn_launch_linear(a, (cudaStream_t)stream);
 }
 
-static LinearArgs lin1(const float* x, const int32_t* idx, const float* W, const float* gamma, const float* beta,
-                       const float* res, int flags, float* out, int64_t m) {
+LinearArgs lgcn_lin1(const float* x, const int32_t* idx, const float* W, const float* gamma, const float* beta,
+                     const float* res, int flags, float* out, int64_t m, const int32_t* m_dev) {
   LinearArgs a;
   memset(&a, 0, sizeof(a));
   a.a[0] = x; a.idx[0] = idx; a.n_src = 1; a.W = W; a.n_out_blocks = 1;
-  a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = LGCN_C; a.m = m;
+  a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = LGCN_C; a.m = m; a.m_dev = m_dev;
   a.dbg = g_debug;
   return a;
+}
+static LinearArgs lin1(const float* x, const int32_t* idx, const float* W, const float* gamma, const float* beta,
+                       const float* res, int flags, float* out, int64_t m) {
+  return lgcn_lin1(x, idx, W, gamma, beta, res, flags, out, m, nullptr);
 }
 
 // ------------------------------------------------------------------ LaneConv stack
@@ -209,6 +216,35 @@ extern "C" int64_t lgcn_laneconv_planned_workspace_bytes(int64_t n_nodes, int64_
 #endif
 }
 
+// blocks of the stack on weights that are ALREADY split (w_hi / w_lo: tf32 hi / lo images of the whole wpack, norm
+// vectors included at their places); `other` [n,128] and `xa` (aux rows) are scratch.  n_dev: live row count in
+// device memory (n_nodes is then the capacity).
+int lgcn_laneconv_stack_presplit(float* feat, float* other, float* xa, void* plan, int64_t n_edges, int n_keys,
+                                 int n_blocks, const float* wpack, const float* w_hi, const float* w_lo, int64_t n_nodes,
+                                 const int32_t* n_dev, cudaStream_t st) {
+#if LGCN_HAVE_TC
+  const int nb = n_keys + 1;
+  const int64_t per = lgcn_laneconv_wpack_floats(n_keys);
+  for (int i = 0; i < n_blocks; ++i) {
+    const float* w = wpack + (int64_t)i * per;   // Wcat | Wctr2 | 4 norm vectors
+    const float* gn = w + (int64_t)(nb + 1) * CC;
+    const float* src = (i & 1) ? other : feat;
+    float* dst = (i & 1) ? feat : other;
+    LgcnProfScope ps(LGCN_PROF_FUSED, st);
+    if (int rc = lgcn_launch_laneconv_fused(src, dst, plan, n_nodes, n_dev, n_edges, n_keys, w_hi + (int64_t)i * per,
+                                            w_lo + (int64_t)i * per, gn, xa, 1, st))
+      return rc;
+  }
+  if (n_blocks & 1) LGCN_CUDA_OK(cudaMemcpyAsync(feat, other, n_nodes * LGCN_C * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+#else
+  (void)feat; (void)other; (void)xa; (void)plan; (void)n_edges; (void)n_keys; (void)n_blocks; (void)wpack; (void)w_hi;
+  (void)w_lo; (void)n_nodes; (void)n_dev; (void)st;
+  LGCN_CHECK_ARG(false, "laneconv_stack_planned: built without the tcgen05 engine");
+  return -1;
+#endif
+}
+
 extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_edges, int n_keys, int n_blocks,
                                            const float* wpack, int64_t n_nodes, void* workspace, void* stream) {
 #if LGCN_HAVE_TC
@@ -218,7 +254,6 @@ extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_ed
   LGCN_CHECK_ARG(lgcn_get_gemm_engine() == 1, "laneconv_stack_planned needs the tcgen05 engine");
   if (n_nodes <= 0 || n_blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nb = n_keys + 1;
   const int64_t per = lgcn_laneconv_wpack_floats(n_keys);
   float* other = (float*)workspace;
   float* xa = (float*)((char*)other + lgcn_align_up(n_nodes * LGCN_C * 4, 1024));
@@ -226,18 +261,8 @@ extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_ed
   float* w_lo = (float*)((char*)w_hi + lgcn_align_up(LGCN_MAX_PLANNED_BLOCKS * per * 4, 1024));
   // the whole pack (weights and, harmlessly, the norm vectors between them) is split by one launch
   if (int rc = lgcn_split_tf32(wpack, w_hi, w_lo, (int64_t)n_blocks * per, st)) return rc;
-  for (int i = 0; i < n_blocks; ++i) {
-    const float* w = wpack + (int64_t)i * per;   // Wcat | Wctr2 | 4 norm vectors
-    const float* gn = w + (int64_t)(nb + 1) * CC;
-    const float* src = (i & 1) ? other : feat;
-    float* dst = (i & 1) ? feat : other;
-    LgcnProfScope ps(LGCN_PROF_FUSED, st);
-    if (int rc = lgcn_launch_laneconv_fused(src, dst, plan, n_nodes, n_edges, n_keys, w_hi + (int64_t)i * per,
-                                            w_lo + (int64_t)i * per, gn, xa, 1, st))
-      return rc;
-  }
-  if (n_blocks & 1) LGCN_CUDA_OK(cudaMemcpyAsync(feat, other, n_nodes * LGCN_C * 4, cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return lgcn_laneconv_stack_presplit(feat, other, xa, plan, n_edges, n_keys, n_blocks, wpack, w_hi, w_lo, n_nodes,
+                                      nullptr, st);
 #else
   (void)feat; (void)plan; (void)n_edges; (void)n_keys; (void)n_blocks; (void)wpack; (void)n_nodes; (void)workspace; (void)stream;
   LGCN_CHECK_ARG(false, "laneconv_stack_planned: built without the tcgen05 engine");
@@ -278,13 +303,29 @@ extern "C" int64_t lgcn_att_workspace_bytes(int64_t n_agt, int64_t n_pairs) {
   return 3 * lgcn_align_up(n_pairs * LGCN_C * 4, 1024) + 2 * lgcn_align_up(n_agt * LGCN_C * 4, 1024) + 2 * 8 * CC * 4 + 1024;
 }
 
-extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs,
-                                const float* ctx_ctrs, const int32_t* hi, const int32_t* wi,
-                                const int32_t* rowptr, int64_t n_agt, int64_t n_ctx, int64_t n_pairs,
-                                const float* wpack, void* workspace, void* stream) {
-  LGCN_CHECK_ARG(agts_in && agts_out && wpack && workspace, "att_forward: NULL argument");
+// The six weight matrices of an Att layer as 8 tf32 hi / lo blocks (ONE launch):
+// 0 dist.2 | 1 query | 2-4 ctx.0 (its three K=128 slices) | 5 ctx.1 | 6 agt | 7 linear
+int lgcn_att_split_weights(const float* wpack, float* WH, float* WL, cudaStream_t st) {
+  const AttW w = att_unpack(wpack);
+  LgcnSplitList sl;
+  const float* ps[8] = {w.d2w, w.qw, w.c0w, w.c0w + LGCN_C, w.c0w + 2 * LGCN_C, w.c1w, w.aw, w.lw};
+  for (int b = 0; b < 8; ++b) {
+    sl.p[b] = ps[b];
+    sl.ldw[b] = (b >= 2 && b <= 4) ? 3 * LGCN_C : LGCN_C;
+  }
+  sl.n_blocks = 8;
+  return lgcn_split_blocks_many(sl, WH, WL, st);
+}
+
+// One Att layer with every size either by value or in device memory (n_agt_dev / n_pairs_dev != NULL: n_agt / n_pairs
+// are capacities).  WH / WL: the layer's pre-split weights (lgcn_att_split_weights) or NULL on the fp32 SIMT engine.
+// scratch: P0 P1 P2 [n_pairs,128] | A0 A1 [n_agt,128] (lgcn_att_workspace_bytes layout).  n_ctx == 0 selects the
+// reference's early-out (lanegcn.py:664-670) and is a host-side decision.
+int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs, const float* ctx_ctrs,
+                   const int32_t* hi, const int32_t* wi, const int32_t* rowptr, int64_t n_agt, const int32_t* n_agt_dev,
+                   int64_t n_ctx, int64_t n_pairs, const int32_t* n_pairs_dev, const float* wpack, const float* WH,
+                   const float* WL, void* workspace, cudaStream_t st) {
   if (n_agt <= 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
   LgcnProfScope ps(LGCN_PROF_ATT, st);
   const AttW w = att_unpack(wpack);
   const int64_t pb = lgcn_align_up(n_pairs * LGCN_C * 4, 1024), ab = lgcn_align_up(n_agt * LGCN_C * 4, 1024);
@@ -294,21 +335,7 @@ extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const flo
   float* A0 = (float*)((char*)workspace + 3 * pb);
   float* A1 = (float*)((char*)workspace + 3 * pb + ab);
   const int kLin = LGCN_EPI_GN | LGCN_EPI_RES | LGCN_EPI_RELU2;
-  // the six weight matrices of the layer as 8 tf32 hi / lo blocks, split by ONE launch (tcgen05 engine only):
-  // 0 dist.2 | 1 query | 2-4 ctx.0 (its three K=128 slices) | 5 ctx.1 | 6 agt | 7 linear
-  float* WH = (float*)((char*)workspace + 3 * pb + 2 * ab);
-  float* WL = WH + 8 * CC;
-  const bool pre = lgcn_get_gemm_engine() == 1;
-  if (pre) {
-    LgcnSplitList sl;
-    const float* ps[8] = {w.d2w, w.qw, w.c0w, w.c0w + LGCN_C, w.c0w + 2 * LGCN_C, w.c1w, w.aw, w.lw};
-    for (int b = 0; b < 8; ++b) {
-      sl.p[b] = ps[b];
-      sl.ldw[b] = (b >= 2 && b <= 4) ? 3 * LGCN_C : LGCN_C;
-    }
-    sl.n_blocks = 8;
-    if (int rc = lgcn_split_blocks_many(sl, WH, WL, st)) return rc;
-  }
+  const bool pre = WH != nullptr && WL != nullptr;
   auto with_w = [&](LinearArgs a, int blk) {
     if (pre) {
       a.w_hi = WH + (int64_t)blk * CC;
@@ -316,44 +343,66 @@ extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const flo
     }
     return a;
   };
+  auto agt_rows = [&](const float* x, const int32_t* idx, const float* W, const float* g, const float* b, const float* res,
+                      int flags, float* out) { return lgcn_lin1(x, idx, W, g, b, res, flags, out, n_agt, n_agt_dev); };
+  auto pair_rows = [&](const float* x, const int32_t* idx, const float* W, const float* g, const float* b, const float* res,
+                       int flags, float* out) { return lgcn_lin1(x, idx, W, g, b, res, flags, out, n_pairs, n_pairs_dev); };
   if (n_ctx == 0) {  // lanegcn.py:664-670 — no self.norm on this path
-    LinearArgs a = with_w(lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, LGCN_EPI_RELU1, A0, n_agt), 6);
+    LinearArgs a = with_w(agt_rows(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, LGCN_EPI_RELU1, A0), 6);
     if (int rc = lgcn_launch_linear(a, st)) return rc;
-    LinearArgs l = with_w(lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt), 7);
+    LinearArgs l = with_w(agt_rows(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out), 7);
     return lgcn_launch_linear(l, st);
   }
   LGCN_CHECK_ARG(n_pairs > 0, "att_forward: no agent/context pair within the distance threshold in any scene "
                               "(the reference raises at lanegcn.py:688: torch.cat of an empty list)");
   LGCN_CHECK_ARG(ctx && agt_ctrs && ctx_ctrs && hi && wi && rowptr, "att_forward: NULL argument");
   // dist = relu(GN(L(relu(L2(agt_ctrs[hi] - ctx_ctrs[wi])))))                      lanegcn.py:693-694
-  if (int rc = lgcn_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, stream)) return rc;
-  LinearArgs d2 = with_w(lin1(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1, n_pairs), 0);
+  if (int rc = lgcn_launch_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, n_pairs_dev, st)) return rc;
+  LinearArgs d2 = with_w(pair_rows(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1), 0);
   if (int rc = lgcn_launch_linear(d2, st)) return rc;
   // query = relu(GN(L(agts[hi])))  — a per-row function: computed per agent when that is fewer rows   :696
+  // (decided on the capacities when the sizes live on the device)
   const float* q;
   const int32_t* qidx;
   if (n_agt <= n_pairs) {
-    LinearArgs qa = with_w(lin1(agts_in, nullptr, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, A0, n_agt), 1);
+    LinearArgs qa = with_w(agt_rows(agts_in, nullptr, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, A0), 1);
     if (int rc = lgcn_launch_linear(qa, st)) return rc;
     q = A0; qidx = hi;
   } else {
-    LinearArgs qp = with_w(lin1(agts_in, hi, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P2, n_pairs), 1);
+    LinearArgs qp = with_w(pair_rows(agts_in, hi, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P2), 1);
     if (int rc = lgcn_launch_linear(qp, st)) return rc;
     q = P2; qidx = nullptr;
   }
   // ctx = L(relu(GN(L384(cat(dist, query, ctx[wi])))))  — split-K over the three sources, no cat   :698-700
-  LinearArgs c0 = with_w(lin1(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0, n_pairs), 2);
+  LinearArgs c0 = with_w(pair_rows(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0), 2);
   c0.n_src = 3;
   c0.a[1] = q; c0.idx[1] = qidx;
   c0.a[2] = ctx; c0.idx[2] = wi;
   if (int rc = lgcn_launch_linear(c0, st)) return rc;
-  LinearArgs c1 = with_w(lin1(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1, n_pairs), 5);
+  LinearArgs c1 = with_w(pair_rows(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1), 5);
   if (int rc = lgcn_launch_linear(c1, st)) return rc;
   // agts = relu(GN(agt(agts) + scatter(ctx by hi)))                                                  :702-705
-  LinearArgs ag = with_w(lin1(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1, n_agt), 6);
+  LinearArgs ag = with_w(agt_rows(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1), 6);
   if (int rc = lgcn_launch_linear(ag, st)) return rc;
-  if (int rc = lgcn_segsum_gn_relu(A1, P1, rowptr, w.ng, w.nb, A0, n_agt, stream)) return rc;
+  if (int rc = lgcn_launch_segsum_gn_relu(A1, P1, rowptr, w.ng, w.nb, A0, n_agt, n_agt_dev, st)) return rc;
   // agts = relu(GN(linear(agts)) + res)                                                              :707-709
-  LinearArgs l = with_w(lin1(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out, n_agt), 7);
+  LinearArgs l = with_w(agt_rows(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out), 7);
   return lgcn_launch_linear(l, st);
+}
+
+extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs,
+                                const float* ctx_ctrs, const int32_t* hi, const int32_t* wi,
+                                const int32_t* rowptr, int64_t n_agt, int64_t n_ctx, int64_t n_pairs,
+                                const float* wpack, void* workspace, void* stream) {
+  LGCN_CHECK_ARG(agts_in && agts_out && wpack && workspace, "att_forward: NULL argument");
+  if (n_agt <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t pb = lgcn_align_up(n_pairs * LGCN_C * 4, 1024), ab = lgcn_align_up(n_agt * LGCN_C * 4, 1024);
+  float* WH = (float*)((char*)workspace + 3 * pb + 2 * ab);
+  float* WL = WH + 8 * CC;
+  const bool pre = lgcn_get_gemm_engine() == 1;
+  if (pre)
+    if (int rc = lgcn_att_split_weights(wpack, WH, WL, st)) return rc;
+  return lgcn_att_layer(agts_in, agts_out, ctx, agt_ctrs, ctx_ctrs, hi, wi, rowptr, n_agt, nullptr, n_ctx, n_pairs, nullptr,
+                        wpack, pre ? WH : nullptr, pre ? WL : nullptr, workspace, st);
 }

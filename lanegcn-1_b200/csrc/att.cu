@@ -2,16 +2,6 @@
 // host sync) and the K=2 "first layer" MLP heads (lanegcn.py:277-286, 644-648, 693).
 #include "common.cuh"
 
-// scene owning global row r: largest b with off[b] <= r (off is ascending, may contain empty scenes)
-__device__ __forceinline__ int scene_of(const int32_t* __restrict__ off, int n_scenes, int32_t r) {
-  int lo = 0, hi = n_scenes;  // invariant: off[lo] <= r < off[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (off[mid] <= r) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 // Bit-exact restatement of torch's  sqrt(((a - c) ** 2).sum(2)) <= th  in fp32: every operation rounded
 // separately (nvcc would otherwise contract dx*dx + dy*dy into an FMA and flip borderline pairs).
 __device__ __forceinline__ bool within(float ax, float ay, float cx, float cy, float th) {
@@ -23,17 +13,21 @@ __device__ __forceinline__ bool within(float ax, float ay, float cx, float cy, f
 #define PAIR_WARPS 8
 
 // FILL == false: cnt[r] = number of context rows of r's scene within th.
-// FILL == true : write the pairs of row r at row_start[r].., hi = local row + hi_off[b], wi = j + wi_off[b].
+// FILL == true : write the pairs of row r at row_start[r].., hi = local row + hi_off[b], wi = j + wi_off[b]; entries at
+//                positions >= p_cap are dropped (the caller learns about the overflow through p_total / status).
+// The agent row count may live in device memory (n_agt_dev); the scene tables are padded to n_scenes entries with
+// empty scenes (off[b] = total), so the scene count itself never has to.
 template <bool FILL>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pairs(const float2* __restrict__ agt_ctrs, const float2* __restrict__ ctx_ctrs,
         const int32_t* __restrict__ agt_off, const int32_t* __restrict__ ctx_off, int n_scenes,
-        int64_t n_agt, float th, int32_t* __restrict__ cnt, const int32_t* __restrict__ row_start,
-        const int32_t* __restrict__ hi_off, const int32_t* __restrict__ wi_off, int32_t* __restrict__ hi32,
-        int32_t* __restrict__ wi32, int64_t* __restrict__ hi64, int64_t* __restrict__ wi64) {
+        int64_t n_agt_cap, const int32_t* __restrict__ n_agt_dev, float th, int32_t* __restrict__ cnt,
+        const int32_t* __restrict__ row_start, const int32_t* __restrict__ hi_off, const int32_t* __restrict__ wi_off,
+        int32_t* __restrict__ hi32, int32_t* __restrict__ wi32, int64_t* __restrict__ hi64, int64_t* __restrict__ wi64,
+        int64_t p_cap) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
-  if (r >= n_agt) return;
+  if (r >= lgcn_devn(n_agt_dev, n_agt_cap)) return;
   const int b = scene_of(agt_off, n_scenes, (int32_t)r);
   const int32_t c0 = ctx_off[b], c1 = ctx_off[b + 1];
   const float2 a = agt_ctrs[r];
@@ -55,10 +49,12 @@ k_pairs(const float2* __restrict__ agt_ctrs, const float2* __restrict__ ctx_ctrs
     const unsigned m = __ballot_sync(0xffffffffu, p);
     if (FILL && p) {
       const int32_t o = pos + run + __popc(m & ((1u << lane) - 1u));
-      if (hi32) hi32[o] = h;
-      if (wi32) wi32[o] = j + w0;
-      if (hi64) hi64[o] = h;
-      if (wi64) wi64[o] = j + w0;
+      if (o < p_cap) {
+        if (hi32) hi32[o] = h;
+        if (wi32) wi32[o] = j + w0;
+        if (hi64) hi64[o] = h;
+        if (wi64) wi64[o] = j + w0;
+      }
     }
     run += __popc(m);
   }
@@ -131,18 +127,33 @@ k_pairs_scene_offsets(const int32_t* __restrict__ row_start, const int32_t* __re
 }
 
 // destination-indexed rowptr: d = r - agt_off[b] + hi_off[b] for rows of scenes that have pairs (monotone,
-// injective); rows past the last used destination point at P.
+// injective); rows past the last used destination point at P.  With a pair capacity (p_cap >= 0) every entry is
+// clamped to it, *p_total receives min(P, p_cap), and status[0] gets `overflow_bit` if P > p_cap or `empty_bit` if
+// P == 0 (the reference raises there, lanegcn.py:688) — the caller reads status when it next synchronises.
 __global__ void k_pairs_rowptr_dst(const int32_t* __restrict__ row_start, const int32_t* __restrict__ agt_off,
-                                   int n_scenes, int64_t n_agt, int keep_quirk, const int32_t* __restrict__ hi_off,
-                                   const int32_t* __restrict__ used_rows, int32_t* __restrict__ rowptr_dst) {
+                                   int n_scenes, int64_t n_agt_cap, const int32_t* __restrict__ n_agt_dev,
+                                   int keep_quirk, const int32_t* __restrict__ hi_off,
+                                   const int32_t* __restrict__ used_rows, int32_t* __restrict__ rowptr_dst,
+                                   int64_t p_cap, int32_t* __restrict__ p_total, int32_t* __restrict__ status,
+                                   int32_t* __restrict__ p_exact, int overflow_bit, int empty_bit) {
+  const int64_t n_agt = lgcn_devn(n_agt_dev, n_agt_cap);
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n_agt) return;
   const int32_t P = row_start[n_agt];
-  if (r >= *used_rows) rowptr_dst[r] = P;  // includes r == n_agt
+  const int32_t lim = (p_cap >= 0 && P > p_cap) ? (int32_t)p_cap : P;
+  if (r >= *used_rows) rowptr_dst[r] = lim;  // includes r == n_agt
   if (r < n_agt) {
     const int b = scene_of(agt_off, n_scenes, (int32_t)r);
     const int32_t tot = row_start[agt_off[b + 1]] - row_start[agt_off[b]];
-    if (!keep_quirk || tot > 0) rowptr_dst[r - agt_off[b] + hi_off[b]] = row_start[r];
+    if (!keep_quirk || tot > 0) rowptr_dst[r - agt_off[b] + hi_off[b]] = min(row_start[r], lim);
+  }
+  if (r == n_agt) {
+    if (p_total) *p_total = lim;
+    if (p_exact) *p_exact = P;
+    if (status) {
+      if (P > lim) atomicOr(status, overflow_bit);
+      if (P == 0) atomicOr(status, empty_bit);
+    }
   }
 }
 
@@ -154,33 +165,53 @@ extern "C" int64_t lgcn_pairs_workspace_bytes(int64_t n_agt, int n_scenes) {
   return 4 * pairs_ws_ints(n_agt, n_scenes) + 256;
 }
 
-extern "C" int lgcn_pairs_count(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off,
-                                const int32_t* ctx_off, int n_scenes, int64_t n_agt, float th, int keep_quirk,
-                                int32_t* rowptr, void* workspace, int64_t* h_total, void* stream) {
-  LGCN_CHECK_ARG(n_scenes >= 1 && n_agt >= 0, "pairs_count: n_scenes %d n_agt %lld", n_scenes, (long long)n_agt);
-  LGCN_CHECK_ARG(n_agt < (int64_t)1 << 31, "pairs_count: n_agt exceeds int32");
-  cudaStream_t st = (cudaStream_t)stream;
+// count (+ fill when hi32 / wi32 / hi64 / wi64 are given and p_cap >= 0): the whole pair list without a host round
+// trip.  *status: flag bits (OR-ed in); *p_total = min(P, p_cap) drives the consumers; *p_exact = P.
+int lgcn_launch_pairs(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off, const int32_t* ctx_off,
+                      int n_scenes, int64_t n_agt_cap, const int32_t* n_agt_dev, float th, int keep_quirk,
+                      int32_t* rowptr, void* workspace, int64_t p_cap, int32_t* hi32, int32_t* wi32, int32_t* p_total,
+                      int32_t* status, int32_t* p_exact, int overflow_bit, int empty_bit, cudaStream_t st) {
+  LGCN_CHECK_ARG(n_scenes >= 1 && n_agt_cap >= 0, "pairs: n_scenes %d n_agt %lld", n_scenes, (long long)n_agt_cap);
+  LGCN_CHECK_ARG(n_agt_cap < (int64_t)1 << 31, "pairs: n_agt exceeds int32");
   int32_t* row_start = (int32_t*)workspace;
-  int32_t* hi_off = row_start + lgcn_align_up(n_agt + 1, 64);
+  int32_t* hi_off = row_start + lgcn_align_up(n_agt_cap + 1, 64);
   int32_t* wi_off = hi_off + lgcn_align_up(n_scenes, 64);
   int32_t* cnt = wi_off + lgcn_align_up(n_scenes, 64);
-  if (n_agt > 0) {
-    k_pairs<false><<<lgcn_cdiv(n_agt, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(
-        (const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, th, cnt, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  const unsigned grid = lgcn_cdiv(n_agt_cap, PAIR_WARPS);
+  if (n_agt_cap > 0) {
+    k_pairs<false><<<grid, PAIR_WARPS * 32, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off,
+                                                     n_scenes, n_agt_cap, n_agt_dev, th, cnt, nullptr, nullptr, nullptr,
+                                                     nullptr, nullptr, nullptr, nullptr, 0);
     LGCN_LAUNCH_OK();
   }
-  int32_t* scratch = cnt + lgcn_align_up(n_agt, 64);  // [0..1024] scan scratch, [1056] used_rows
-  if (lgcn_launch_exclusive_scan(cnt, row_start, n_agt, scratch, st)) return -2;
+  int32_t* scratch = cnt + lgcn_align_up(n_agt_cap, 64);  // [0..1024] scan scratch, [1056] used_rows
+  if (lgcn_launch_exclusive_scan(cnt, row_start, n_agt_cap, n_agt_dev, scratch, st)) return -2;
   k_pairs_scene_offsets<<<1, 1024, 0, st>>>(row_start, agt_off, ctx_off, n_scenes, keep_quirk, hi_off, wi_off,
                                             scratch + 1056);
   LGCN_LAUNCH_OK();
-  k_pairs_rowptr_dst<<<lgcn_cdiv(n_agt + 1, 256), 256, 0, st>>>(row_start, agt_off, n_scenes, n_agt, keep_quirk, hi_off,
-                                                               scratch + 1056, rowptr);
+  k_pairs_rowptr_dst<<<lgcn_cdiv(n_agt_cap + 1, 256), 256, 0, st>>>(row_start, agt_off, n_scenes, n_agt_cap, n_agt_dev,
+                                                                   keep_quirk, hi_off, scratch + 1056, rowptr, p_cap,
+                                                                   p_total, status, p_exact, overflow_bit, empty_bit);
   LGCN_LAUNCH_OK();
+  if (p_cap >= 0 && n_agt_cap > 0 && (hi32 || wi32)) {
+    k_pairs<true><<<grid, PAIR_WARPS * 32, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off,
+                                                    n_scenes, n_agt_cap, n_agt_dev, th, nullptr, row_start, hi_off, wi_off,
+                                                    hi32, wi32, nullptr, nullptr, p_cap);
+    LGCN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int lgcn_pairs_count(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off,
+                                const int32_t* ctx_off, int n_scenes, int64_t n_agt, float th, int keep_quirk,
+                                int32_t* rowptr, void* workspace, int64_t* h_total, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = lgcn_launch_pairs(agt_ctrs, ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, nullptr, th, keep_quirk, rowptr,
+                                 workspace, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, st))
+    return rc;
   if (h_total) {
     int32_t p = 0;
-    LGCN_CUDA_OK(cudaMemcpyAsync(&p, row_start + n_agt, 4, cudaMemcpyDeviceToHost, st));
+    LGCN_CUDA_OK(cudaMemcpyAsync(&p, (int32_t*)workspace + n_agt, 4, cudaMemcpyDeviceToHost, st));
     LGCN_CUDA_OK(cudaStreamSynchronize(st));
     *h_total = p;
   }
@@ -196,8 +227,8 @@ extern "C" int lgcn_pairs_fill(const float* agt_ctrs, const float* ctx_ctrs, con
   const int32_t* hi_off = row_start + lgcn_align_up(n_agt + 1, 64);
   const int32_t* wi_off = hi_off + lgcn_align_up(n_scenes, 64);
   k_pairs<true><<<lgcn_cdiv(n_agt, PAIR_WARPS), PAIR_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, th, nullptr,
-      row_start, hi_off, wi_off, hi32, wi32, hi64, wi64);
+      (const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, nullptr, th, nullptr,
+      row_start, hi_off, wi_off, hi32, wi32, hi64, wi64, (int64_t)1 << 40);
   LGCN_LAUNCH_OK();
   return 0;
 }
@@ -207,8 +238,9 @@ extern "C" int lgcn_pairs_fill(const float* agt_ctrs, const float* ctx_ctrs, con
 __global__ void __launch_bounds__(256)
 k_mlp2_in(const float2* __restrict__ p, const int32_t* __restrict__ ip, const float2* __restrict__ q,
           const int32_t* __restrict__ iq, const float* __restrict__ W1, const float* __restrict__ b1,
-          float* __restrict__ h, int64_t m) {
+          float* __restrict__ h, int64_t m_cap, const int32_t* __restrict__ m_dev) {
   const int lane = threadIdx.x & 31;
+  const int64_t m = lgcn_devn(m_dev, m_cap);
   // W1 is [128,2] row-major: this lane's 4 output channels are rows lane*4..lane*4+3 = 8 contiguous floats
   const float4 w01 = reinterpret_cast<const float4*>(W1)[lane * 2];
   const float4 w23 = reinterpret_cast<const float4*>(W1)[lane * 2 + 1];
@@ -263,11 +295,16 @@ extern "C" int lgcn_mlp4_in(const float* p, const int32_t* ip, const float* q, c
   return 0;
 }
 
-extern "C" int lgcn_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq,
-                            const float* W1, const float* b1, float* h, int64_t m, void* stream) {
-  if (m <= 0) return 0;
-  const unsigned grid = min(lgcn_cdiv(m, 8), 148u * 32u);
-  k_mlp2_in<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)p, ip, (const float2*)q, iq, W1, b1, h, m);
+int lgcn_launch_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
+                        const float* b1, float* h, int64_t m_cap, const int32_t* m_dev, cudaStream_t st) {
+  if (m_cap <= 0) return 0;
+  const unsigned grid = min(lgcn_cdiv(m_cap, 8), 148u * 32u);
+  k_mlp2_in<<<grid, 256, 0, st>>>((const float2*)p, ip, (const float2*)q, iq, W1, b1, h, m_cap, m_dev);
   LGCN_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int lgcn_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq,
+                            const float* W1, const float* b1, float* h, int64_t m, void* stream) {
+  return lgcn_launch_mlp2_in(p, ip, q, iq, W1, b1, h, m, nullptr, (cudaStream_t)stream);
 }

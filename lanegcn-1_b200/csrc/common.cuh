@@ -47,6 +47,24 @@ struct LgcnProfScope {
 static inline int64_t lgcn_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned lgcn_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
+// Row counts of the forward path may live in DEVICE memory (so that a whole forward is one CUDA graph per capacity
+// bucket and no host round trip carries a data-dependent size): n = n_dev ? min(*n_dev, cap) : cap.
+__device__ __forceinline__ int64_t lgcn_devn(const int32_t* n_dev, int64_t cap) {
+  if (!n_dev) return cap;
+  const int64_t n = *n_dev;
+  return n < cap ? (n < 0 ? 0 : n) : cap;
+}
+
+// scene owning global row r: largest b with off[b] <= r (off is ascending, may contain empty scenes)
+__device__ __forceinline__ int scene_of(const int32_t* __restrict__ off, int n_scenes, int32_t r) {
+  int lo = 0, hi = n_scenes;  // invariant: off[lo] <= r < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= r) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -93,6 +111,7 @@ struct LinearArgs {
   float* out;
   int64_t ldo;
   int64_t m;
+  const int32_t* m_dev;  // optional: live row count in device memory (m is then the capacity); one output block only
   int dbg;  // ablation switches for profiling (lgcn_debug_flags); 0 in production
   // optional: the weights already split into tf32 hi / lo blocks [n_src*128, 128] (lgcn_split_blocks_many); when
   // NULL the tcgen05 path splits W into a scratch slot at launch
@@ -115,8 +134,27 @@ struct LgcnSplitList {
   int n_blocks;
 };
 int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st);
-int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, int64_t n_edges, int n_keys,
-                               const float* w_hi, const float* w_lo, const float* gn, float* xa, int chain,
-                               cudaStream_t st);
+int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, const int32_t* n_dev,
+                               int64_t n_edges, int n_keys, const float* w_hi, const float* w_lo, const float* gn,
+                               float* xa, int chain, cudaStream_t st);
 // exclusive scan: out[0..n] (n+1 entries) from cnt[0..n); scratch >= 1025 int32
-int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, int32_t* scratch, cudaStream_t st);
+int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n_cap, const int32_t* n_dev, int32_t* scratch,
+                               cudaStream_t st);
+// ---- launchers whose row counts may live in device memory (n_dev != NULL: n_cap is the capacity that sizes the grid)
+int lgcn_launch_pack_meta(const float* turn, const float* control, const float* intersect, float* meta, int64_t n_cap,
+                          const int32_t* n_dev, cudaStream_t st);
+int lgcn_launch_actor_transpose(const float* in, float* out, int64_t n_cap, const int32_t* n_dev, int T, int C,
+                                cudaStream_t st);
+int lgcn_launch_csr_from_segs(const int64_t* e64, const int64_t* seg_start, int seg_stride, int n_keys, int64_t E_cap,
+                              int64_t n_cap, const int32_t* n_dev, int32_t* rowptr, int32_t* col, void* workspace,
+                              int32_t* err_flag, cudaStream_t st);
+int lgcn_launch_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes, const int32_t* n_dev,
+                           int64_t n_edges, void* plan, cudaStream_t st);
+int lgcn_launch_pairs(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off, const int32_t* ctx_off,
+                      int n_scenes, int64_t n_agt_cap, const int32_t* n_agt_dev, float th, int keep_quirk,
+                      int32_t* rowptr, void* workspace, int64_t p_cap, int32_t* hi32, int32_t* wi32, int32_t* p_total,
+                      int32_t* status, int32_t* p_exact, int overflow_bit, int empty_bit, cudaStream_t st);
+int lgcn_launch_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
+                        const float* b1, float* h, int64_t m_cap, const int32_t* m_dev, cudaStream_t st);
+int lgcn_launch_segsum_gn_relu(const float* a, const float* c, const int32_t* rowptr, const float* gamma,
+                               const float* beta, float* out, int64_t n_cap, const int32_t* n_dev, cudaStream_t st);

@@ -146,7 +146,7 @@ extern "C" int lgcn_dilate_csr0(const int64_t* u, const int64_t* v, int64_t n_ed
     k_d_hist<<<eb, 256, 0, st>>>(u, v, n_edges, n_nodes, cnt, err);
     LGCN_LAUNCH_OK();
   }
-  if (lgcn_launch_exclusive_scan(cnt, raw_ptr, n_nodes, scan_scratch, st)) return -2;
+  if (lgcn_launch_exclusive_scan(cnt, raw_ptr, n_nodes, nullptr, scan_scratch, st)) return -2;
   if (eb) {
     LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)(n_nodes + 1), st));
     k_d_place<<<eb, 256, 0, st>>>(u, v, n_edges, n_nodes, raw_ptr, cnt, raw_col);
@@ -156,7 +156,7 @@ extern "C" int lgcn_dilate_csr0(const int64_t* u, const int64_t* v, int64_t n_ed
     k_d_sort_unique<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(n_nodes, raw_ptr, raw_col, cnt);
     LGCN_LAUNCH_OK();
   }
-  if (lgcn_launch_exclusive_scan(cnt, rowptr, n_nodes, scan_scratch, st)) return -2;
+  if (lgcn_launch_exclusive_scan(cnt, rowptr, n_nodes, nullptr, scan_scratch, st)) return -2;
   if (n_nodes) {
     k_d_compact<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(n_nodes, raw_ptr, raw_col, rowptr, col);
     LGCN_LAUNCH_OK();
@@ -179,7 +179,7 @@ extern "C" int lgcn_dilate_bound(const int32_t* rowptr, const int32_t* col, int6
     k_d_bound<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(n_nodes, rowptr, col, ub);
     LGCN_LAUNCH_OK();
   }
-  if (lgcn_launch_exclusive_scan(ub, off, n_nodes, scan_scratch, st)) return -2;
+  if (lgcn_launch_exclusive_scan(ub, off, n_nodes, nullptr, scan_scratch, st)) return -2;
   return read_i32(off + n_nodes, h_bound, st);
 }
 
@@ -201,7 +201,7 @@ extern "C" int lgcn_dilate_square(const int32_t* rowptr, const int32_t* col, int
     k_d_discover<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(n_nodes, rowptr, col, off, scratch, cnt);
     LGCN_LAUNCH_OK();
   }
-  if (lgcn_launch_exclusive_scan(cnt, rowptr_out, n_nodes, scan_scratch, st)) return -2;
+  if (lgcn_launch_exclusive_scan(cnt, rowptr_out, n_nodes, nullptr, scan_scratch, st)) return -2;
   if (n_nodes) {
     k_d_emit<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(n_nodes, off, scratch, rowptr_out, col_out, u_out, v_out);
     LGCN_LAUNCH_OK();

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) k_linear_simt(LinearArgs a) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t M = lgcn_devn(a.m_dev, a.m);   // live rows (the grid is sized by the capacity a.m)
   const int ob = blockIdx.y;
   const int64_t ldw = (int64_t)a.n_src * LGCN_C + a.ks;
 
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) k_linear_simt(LinearArgs a) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int64_t m = m0 + lrow + 64 * i;
-      if (m < a.m) {
+      if (m < M) {
         const int64_t r = a.idx[s] ? (int64_t)a.idx[s][m] : m;
         arow[i] = a.a[s] + r * LGCN_C + lk;
       } else {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) k_linear_simt(LinearArgs a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    const bool live = m < a.m;  // dead rows still take part in the shuffles
+    const bool live = m < M;  // dead rows still take part in the shuffles
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = acc[i][j];

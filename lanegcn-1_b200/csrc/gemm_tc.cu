@@ -37,6 +37,8 @@
 //               reads are bandwidth-limited, so every accumulator value should be read exactly once.)  Results are staged as
 //               32x32 fp32 blocks in swizzled shared memory and written with TMA bulk tensor stores (coalesced
 //               128 B rows; rows >= M clipped by the tensor map).
+#include <atomic>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -415,7 +417,6 @@ k_linear_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map) {
   }
 }
 
-bool g_attr_set = false;
 
 }  // namespace
 
@@ -450,13 +451,24 @@ int make_map_2d(CUtensorMap* map, const float* base, int64_t cols, int64_t rows,
 int make_out_map(CUtensorMap* map, float* out, int64_t cols, int64_t rows, int64_t ldo) {
   return make_map_2d(map, out, cols, rows, ldo, 32, 32);
 }
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+bool first_use(int family) {
+  static std::atomic<int> seen[kMaxDevices][kFamCount];
+  return seen[current_device()][family].exchange(1, std::memory_order_acq_rel) == 0;
 }
 }  // namespace tc
 
@@ -467,10 +479,9 @@ int lgcn_launch_linear_tc(const LinearArgs& a, cudaStream_t st) {
   if (a.n_out_blocks == 1 && (a.ks == 0 || a.ks == 4) && !(a.dbg & 32768)) return lgcn_launch_linear_fused(a, st);
   LGCN_CHECK_ARG(a.n_src == 1 || a.n_out_blocks == 1, "linear128(tcgen05): several sources need n_out_blocks == 1");
   // (the LaneConv stack routes its 15-block projection to gemm_tc_wide.cu, which needs pre-split weights)
-  if (!g_attr_set) {
+  LGCN_CHECK_ARG(!a.m_dev, "linear128(tcgen05): a device-side row count needs n_out_blocks == 1");
+  if (first_use(kFamLinearTc))
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    g_attr_set = true;
-  }
   CUtensorMap map;
   if (int rc = make_out_map(&map, a.out, (int64_t)a.n_out_blocks * LGCN_C, a.m, a.ldo)) return rc;
   const int64_t n_tiles = (a.m + kTileM - 1) / kTileM;

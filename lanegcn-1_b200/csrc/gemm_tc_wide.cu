@@ -273,7 +273,6 @@ k_wide_tc(const LinearArgs a, const __grid_constant__ CUtensorMap out_map, const
   }
 }
 
-bool g_attr_set = false;
 
 // hi = tf32(w), lo = tf32(w - hi) for a static weight matrix (once per LaneConv block, ~1 MB)
 __global__ void k_split_tf32(const float4* __restrict__ w, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
@@ -304,10 +303,8 @@ int lgcn_launch_wide_tc(const LinearArgs& a, const float* w_hi, const float* w_l
   if (a.m <= 0) return 0;
   LGCN_CHECK_ARG(a.n_src == 1 && a.idx[0] == nullptr && a.flags == 0 && a.ks == 0 && w_hi && w_lo,
                  "wide projection kernel: one un-gathered source, no epilogue, pre-split weights");
-  if (!g_attr_set) {
+  if (first_use(kFamWideTc))
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_wide_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    g_attr_set = true;
-  }
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, a.out, (int64_t)a.n_out_blocks * LGCN_C, a.m, a.ldo)) return rc;
   if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)a.n_out_blocks * LGCN_C, LGCN_C, 32, kTileN)) return rc;

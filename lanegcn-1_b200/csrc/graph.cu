@@ -31,26 +31,61 @@ extern "C" int lgcn_offset_indices(const void* local, int idx_bytes, const int64
 
 // ------------------------------------------------------------------ meta = cat(turn, control, intersect)
 __global__ void k_pack_meta(const float2* __restrict__ turn, const float* __restrict__ control,
-                            const float* __restrict__ intersect, float4* __restrict__ meta, int64_t n) {
+                            const float* __restrict__ intersect, float4* __restrict__ meta, int64_t n_cap,
+                            const int32_t* __restrict__ n_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= lgcn_devn(n_dev, n_cap)) return;
   const float2 t = turn[i];
   meta[i] = make_float4(t.x, t.y, control[i], intersect[i]);
 }
 
-extern "C" int lgcn_pack_meta(const float* turn, const float* control, const float* intersect, float* meta,
-                              int64_t n, void* stream) {
-  if (n <= 0) return 0;
-  k_pack_meta<<<lgcn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)turn, control, intersect,
-                                                                   (float4*)meta, n);
+int lgcn_launch_pack_meta(const float* turn, const float* control, const float* intersect, float* meta, int64_t n_cap,
+                          const int32_t* n_dev, cudaStream_t st) {
+  if (n_cap <= 0) return 0;
+  k_pack_meta<<<lgcn_cdiv(n_cap, 256), 256, 0, st>>>((const float2*)turn, control, intersect, (float4*)meta, n_cap, n_dev);
   LGCN_LAUNCH_OK();
   return 0;
 }
 
+extern "C" int lgcn_pack_meta(const float* turn, const float* control, const float* intersect, float* meta,
+                              int64_t n, void* stream) {
+  return lgcn_launch_pack_meta(turn, control, intersect, meta, n, nullptr, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ actor_gather (lanegcn.py:155-168)
+// out[a, c, t] = in[a, t, c]: the per-actor transpose of the concatenated [A, T, C] history (T = 20 steps, C = 3:
+// dx, dy, valid) into the channels-first layout ActorNet's Conv1d stack expects.  Pure data movement (bit-exact).
+__global__ void k_actor_transpose(const float* __restrict__ in, float* __restrict__ out, int64_t n_cap,
+                                  const int32_t* __restrict__ n_dev, int T, int C) {
+  const int64_t n = lgcn_devn(n_dev, n_cap);
+  const int64_t per = (int64_t)T * C, total = n * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = i / per;
+    const int r = (int)(i - a * per), c = r / T, t = r - c * T;   // i indexes the OUTPUT (coalesced stores)
+    out[i] = in[a * per + (int64_t)t * C + c];
+  }
+}
+
+int lgcn_launch_actor_transpose(const float* in, float* out, int64_t n_cap, const int32_t* n_dev, int T, int C,
+                                cudaStream_t st) {
+  if (n_cap <= 0) return 0;
+  k_actor_transpose<<<min(lgcn_cdiv(n_cap * T * C, 256), 148u * 8u), 256, 0, st>>>(in, out, n_cap, n_dev, T, C);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lgcn_actor_gather(const float* feats, float* out, int64_t n_actors, int n_steps, int n_channels,
+                                 void* stream) {
+  LGCN_CHECK_ARG(n_actors >= 0 && n_steps > 0 && n_channels > 0, "actor_gather: sizes");
+  LGCN_CHECK_ARG(n_actors == 0 || (feats && out), "actor_gather: NULL argument");
+  return lgcn_launch_actor_transpose(feats, out, n_actors, nullptr, n_steps, n_channels, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ exclusive scan
 // n is at most a few hundred thousand rows.  Three tiny launches: (1) per-block sums of 4096-element chunks,
-// (2) one block scans the <= 1024 chunk sums, (3) every block scans its chunk with its base.  All loads are
-// the array is at most ~1 MB, i.e. L2-resident between the passes.
+// (2) one block scans the <= 1024 chunk sums, (3) every block scans its chunk with its base.  The array is at most
+// a few MB, i.e. L2-resident between the passes.  The element count may live in device memory (n_dev): the grids are
+// sized by the capacity and blocks past the live range have nothing to do.
 #define SCAN_BLOCK 256
 #define SCAN_ITEMS 16  // per thread -> 4096 elements per block
 
@@ -79,8 +114,10 @@ __device__ __forceinline__ int32_t block_inclusive_scan(int32_t v, int32_t* warp
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block_sums(const int32_t* __restrict__ cnt, int32_t* __restrict__ sums, int64_t n) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block_sums(const int32_t* __restrict__ cnt, int32_t* __restrict__ sums,
+                                                                int64_t n_cap, const int32_t* __restrict__ n_dev) {
   __shared__ int32_t wt[32];
+  const int64_t n = lgcn_devn(n_dev, n_cap);
   const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS;
   int32_t s = 0;
 #pragma unroll
@@ -93,18 +130,21 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block_sums(const int32_t* _
   if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ sums, int nb, int32_t* __restrict__ out_total) {
+__global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ sums, int nb, int32_t* __restrict__ out,
+                                                    int64_t n_cap, const int32_t* __restrict__ n_dev) {
   __shared__ int32_t wt[32];
   const int32_t v = threadIdx.x < nb ? sums[threadIdx.x] : 0;
   int32_t total;
   const int32_t inc = block_inclusive_scan(v, wt, &total);
   if (threadIdx.x < nb) sums[threadIdx.x] = inc - v;  // exclusive base of each chunk
-  if (threadIdx.x == 0) *out_total = total;
+  if (threadIdx.x == 0) out[lgcn_devn(n_dev, n_cap)] = total;
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const int32_t* __restrict__ cnt, const int32_t* __restrict__ sums,
-                                                           int32_t* __restrict__ out, int64_t n) {
+                                                           int32_t* __restrict__ out, int64_t n_cap,
+                                                           const int32_t* __restrict__ n_dev) {
   __shared__ int32_t wt[32];
+  const int64_t n = lgcn_devn(n_dev, n_cap);
   const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS;
   int32_t run = sums[blockIdx.x];
   // thread t owns SCAN_ITEMS CONSECUTIVE elements (strided reads hit L2: the array is at most ~1 MB)
@@ -127,24 +167,28 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const int32_t* __rest
 
 // out[0..n] (n+1 entries, out[n] = total).  `scratch` (>= 1025 int32, caller-provided so the call stays
 // re-entrant) holds the chunk sums.
-int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n, int32_t* scratch, cudaStream_t st) {
+int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n_cap, const int32_t* n_dev, int32_t* scratch,
+                               cudaStream_t st) {
   const int64_t per = (int64_t)SCAN_BLOCK * SCAN_ITEMS;
-  const int64_t nb = (n + per - 1) / per;
-  LGCN_CHECK_ARG(nb <= 1024, "exclusive_scan: %lld elements exceed the 4M-element limit", (long long)n);
+  const int64_t nb = (n_cap + per - 1) / per;
+  LGCN_CHECK_ARG(nb <= 1024, "exclusive_scan: %lld elements exceed the 4M-element limit", (long long)n_cap);
   if (nb == 0) {
     LGCN_CUDA_OK(cudaMemsetAsync(out, 0, 4, st));
     return 0;
   }
-  k_scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, n);
+  k_scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, n_cap, n_dev);
   LGCN_LAUNCH_OK();
-  k_scan_sums<<<1, 1024, 0, st>>>(scratch, (int)nb, out + n);
+  k_scan_sums<<<1, 1024, 0, st>>>(scratch, (int)nb, out, n_cap, n_dev);
   LGCN_LAUNCH_OK();
-  k_scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, out, n);
+  k_scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, out, n_cap, n_dev);
   LGCN_LAUNCH_OK();
   return 0;
 }
 
 // ------------------------------------------------------------------ merged destination-sorted CSR
+// The edge sets either come by value (host arrays of device pointers: lgcn_csr_build) or are described in device
+// memory (lgcn_forward: the batched int64 indices and their segment table are produced on the device and their sizes
+// never visit the host).
 struct EdgeSets {
   const int64_t* u[LGCN_MAX_KEYS];
   const int64_t* v[LGCN_MAX_KEYS];
@@ -159,7 +203,25 @@ __device__ __forceinline__ int key_of(const EdgeSets& es, int64_t e) {
   return k;
 }
 
-__global__ void k_csr_hist(EdgeSets es, int64_t n_nodes, int64_t n_src, int32_t* __restrict__ cnt, int32_t* __restrict__ err) {
+// Device-side description of the batched edge sets written by lgcn_offset_indices: `e64` holds, per key k, the
+// segments u_k (seg_stride of them, one per scene slot) then v_k; seg_start[] are element offsets.
+__global__ void k_edge_sets_from_segs(const int64_t* __restrict__ e64, const int64_t* __restrict__ seg_start,
+                                      int seg_stride, int n_keys, EdgeSets* __restrict__ es) {
+  const int k = threadIdx.x;
+  if (k < n_keys) {
+    es->u[k] = e64 + seg_start[(int64_t)(2 * k) * seg_stride];
+    es->v[k] = e64 + seg_start[(int64_t)(2 * k + 1) * seg_stride];
+  }
+  if (k <= n_keys) es->start[k] = seg_start[(int64_t)(2 * k) * seg_stride] / 2;
+  if (k == 0) es->n_keys = n_keys;
+}
+
+template <bool DEV>
+__global__ void k_csr_hist(const EdgeSets es_val, const EdgeSets* __restrict__ es_dev, int64_t n_cap,
+                           const int32_t* __restrict__ n_dev, int64_t n_src_cap, int32_t* __restrict__ cnt,
+                           int32_t* __restrict__ err) {
+  const EdgeSets& es = DEV ? *es_dev : es_val;
+  const int64_t n_nodes = lgcn_devn(n_dev, n_cap), n_src = n_dev ? n_nodes : n_src_cap;
   const int64_t E = es.start[es.n_keys];
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     const int k = key_of(es, e);
@@ -172,8 +234,12 @@ __global__ void k_csr_hist(EdgeSets es, int64_t n_nodes, int64_t n_src, int32_t*
   }
 }
 
-__global__ void k_csr_place(EdgeSets es, int64_t n_nodes, int64_t n_src, const int32_t* __restrict__ rowptr,
+template <bool DEV>
+__global__ void k_csr_place(const EdgeSets es_val, const EdgeSets* __restrict__ es_dev, int64_t n_cap,
+                            const int32_t* __restrict__ n_dev, int64_t n_src_cap, const int32_t* __restrict__ rowptr,
                             int32_t* __restrict__ cursor, int32_t* __restrict__ slot_edge) {
+  const EdgeSets& es = DEV ? *es_dev : es_val;
+  const int64_t n_nodes = lgcn_devn(n_dev, n_cap), n_src = n_dev ? n_nodes : n_src_cap;
   const int64_t E = es.start[es.n_keys];
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     const int k = key_of(es, e);
@@ -188,10 +254,13 @@ __global__ void k_csr_place(EdgeSets es, int64_t n_nodes, int64_t n_src, const i
 // the stable-by-destination order CPU index_add_ accumulates in) and emit col = v*(K+1) + (k+1).
 // Rows are short (about a dozen entries on lane graphs), so an in-place insertion sort is the right tool;
 // the atomics above only decide a scratch order that this pass erases, so the CSR is deterministic.
-__global__ void k_csr_finish(EdgeSets es, int64_t n_nodes, int plain, const int32_t* __restrict__ rowptr,
+template <bool DEV>
+__global__ void k_csr_finish(const EdgeSets es_val, const EdgeSets* __restrict__ es_dev, int64_t n_cap,
+                             const int32_t* __restrict__ n_dev, int plain, const int32_t* __restrict__ rowptr,
                              int32_t* __restrict__ slot_edge, int32_t* __restrict__ col) {
+  const EdgeSets& es = DEV ? *es_dev : es_val;
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_nodes) return;
+  if (r >= lgcn_devn(n_dev, n_cap)) return;
   const int32_t beg = rowptr[r], end = rowptr[r + 1];
   for (int32_t i = beg + 1; i < end; ++i) {
     const int32_t x = slot_edge[i];
@@ -212,8 +281,33 @@ __global__ void k_csr_finish(EdgeSets es, int64_t n_nodes, int plain, const int3
 }
 
 extern "C" int64_t lgcn_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
-  // cnt/cursor int32[n_nodes] + slot_edge int32[n_edges] + scan scratch int32[1025]
-  return lgcn_align_up(4 * n_nodes, 256) + lgcn_align_up(4 * n_edges, 256) + 4352 + 256;
+  // cnt/cursor int32[n_nodes] + slot_edge int32[n_edges] + scan scratch int32[1025] + device EdgeSets
+  return lgcn_align_up(4 * n_nodes, 256) + lgcn_align_up(4 * n_edges, 256) + 4352 + 512 + 256;
+}
+
+template <bool DEV>
+static int csr_launch(const EdgeSets& es, const EdgeSets* es_dev, int64_t E_cap, int64_t n_cap, const int32_t* n_dev,
+                      int64_t n_src, int plain, int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag,
+                      cudaStream_t st) {
+  int32_t* cnt = (int32_t*)workspace;
+  int32_t* slot_edge = (int32_t*)((char*)workspace + lgcn_align_up(4 * n_cap, 256));
+  int32_t* scan_scratch = (int32_t*)((char*)slot_edge + lgcn_align_up(4 * E_cap, 256));
+  LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_cap, st));
+  LGCN_CUDA_OK(cudaMemsetAsync(err_flag, 0, 4, st));
+  const unsigned eb = E_cap ? min(lgcn_cdiv(E_cap, 256), 148u * 16u) : 0u;
+  if (eb) {
+    k_csr_hist<DEV><<<eb, 256, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, cnt, err_flag);
+    LGCN_LAUNCH_OK();
+  }
+  if (lgcn_launch_exclusive_scan(cnt, rowptr, n_cap, n_dev, scan_scratch, st)) return -2;
+  if (eb) {
+    LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_cap, st));
+    k_csr_place<DEV><<<eb, 256, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, rowptr, cnt, slot_edge);
+    LGCN_LAUNCH_OK();
+    k_csr_finish<DEV><<<lgcn_cdiv(n_cap, 128), 128, 0, st>>>(es, es_dev, n_cap, n_dev, plain, rowptr, slot_edge, col);
+    LGCN_LAUNCH_OK();
+  }
+  return 0;
 }
 
 static int csr_build_impl(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len, int n_keys,
@@ -233,25 +327,22 @@ static int csr_build_impl(const int64_t* const* h_u, const int64_t* const* h_v, 
   const int64_t E = es.start[n_keys];
   LGCN_CHECK_ARG(E < (int64_t)1 << 31, "csr_build: %lld edges exceed int32", (long long)E);
   LGCN_CHECK_ARG(n_src * (int64_t)(plain ? 1 : n_keys + 1) < (int64_t)1 << 31, "csr_build: block index exceeds int32");
-  int32_t* cnt = (int32_t*)workspace;
-  int32_t* slot_edge = (int32_t*)((char*)workspace + lgcn_align_up(4 * n_nodes, 256));
-  int32_t* scan_scratch = (int32_t*)((char*)slot_edge + lgcn_align_up(4 * E, 256));
-  LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_nodes, st));
-  LGCN_CUDA_OK(cudaMemsetAsync(err_flag, 0, 4, st));
-  const unsigned eb = E ? min(lgcn_cdiv(E, 256), 148u * 16u) : 0u;
-  if (eb) {
-    k_csr_hist<<<eb, 256, 0, st>>>(es, n_nodes, n_src, cnt, err_flag);
-    LGCN_LAUNCH_OK();
-  }
-  if (lgcn_launch_exclusive_scan(cnt, rowptr, n_nodes, scan_scratch, st)) return -2;
-  if (eb) {
-    LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_nodes, st));
-    k_csr_place<<<eb, 256, 0, st>>>(es, n_nodes, n_src, rowptr, cnt, slot_edge);
-    LGCN_LAUNCH_OK();
-    k_csr_finish<<<lgcn_cdiv(n_nodes, 128), 128, 0, st>>>(es, n_nodes, plain, rowptr, slot_edge, col);
-    LGCN_LAUNCH_OK();
-  }
-  return 0;
+  return csr_launch<false>(es, nullptr, E, n_nodes, nullptr, n_src, plain, rowptr, col, workspace, err_flag, st);
+}
+
+// CSR of the edge sets lgcn_offset_indices wrote (e64 + segment table, seg_stride = scene slots per (key, u|v)):
+// node count in device memory, edge capacity E_cap (half of the index capacity).  Same workspace layout.
+int lgcn_launch_csr_from_segs(const int64_t* e64, const int64_t* seg_start, int seg_stride, int n_keys, int64_t E_cap,
+                              int64_t n_cap, const int32_t* n_dev, int32_t* rowptr, int32_t* col, void* workspace,
+                              int32_t* err_flag, cudaStream_t st) {
+  LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "csr_from_segs: n_keys %d out of range", n_keys);
+  LGCN_CHECK_ARG(E_cap < (int64_t)1 << 31 && n_cap * (int64_t)(n_keys + 1) < (int64_t)1 << 31, "csr_from_segs: sizes exceed int32");
+  EdgeSets* es_dev = (EdgeSets*)((char*)workspace + lgcn_align_up(4 * n_cap, 256) + lgcn_align_up(4 * E_cap, 256) + 4352);
+  k_edge_sets_from_segs<<<1, 32, 0, st>>>(e64, seg_start, seg_stride, n_keys, es_dev);
+  LGCN_LAUNCH_OK();
+  EdgeSets dummy;
+  dummy.n_keys = 0;
+  return csr_launch<true>(dummy, es_dev, E_cap, n_cap, n_dev, n_cap, 0, rowptr, col, workspace, err_flag, st);
 }
 
 extern "C" int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const int64_t* h_len,

@@ -22,10 +22,10 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32)
 k_gather_gn_relu(const float* __restrict__ base, int64_t base_ld, const float* __restrict__ blocks,
                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
-                 int64_t n_rows) {
+                 int64_t n_rows, const int32_t* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
+  if (row >= lgcn_devn(n_dev, n_rows)) return;
   const int32_t beg = rowptr[row], end = rowptr[row + 1];
   float4 acc = ld_stream_f4(base + row * base_ld + lane * 4);
   for (int32_t e0 = beg; e0 < end; e0 += 32) {
@@ -62,7 +62,7 @@ extern "C" int lgcn_laneconv_gather_gn_relu(const float* Y, int n_blocks, const 
   LGCN_CHECK_ARG(n_blocks >= 1, "gather: n_blocks %d", n_blocks);
   if (n_nodes <= 0) return 0;
   k_gather_gn_relu<false><<<lgcn_cdiv(n_nodes, GATHER_WARPS), GATHER_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      Y, (int64_t)n_blocks * LGCN_C, Y, rowptr, col, gamma, beta, out, n_nodes);
+      Y, (int64_t)n_blocks * LGCN_C, Y, rowptr, col, gamma, beta, out, n_nodes, nullptr);
   LGCN_LAUNCH_OK();
   return 0;
 }
@@ -73,16 +73,21 @@ extern "C" int lgcn_gather_rows_gn_relu(const float* base, int64_t base_ld, cons
   LGCN_CHECK_ARG(base_ld >= LGCN_C && base_ld % 4 == 0, "gather_rows: bad base_ld %lld", (long long)base_ld);
   if (n_rows <= 0) return 0;
   k_gather_gn_relu<false><<<lgcn_cdiv(n_rows, GATHER_WARPS), GATHER_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      base, base_ld, blocks, rowptr, col, gamma, beta, out, n_rows);
+      base, base_ld, blocks, rowptr, col, gamma, beta, out, n_rows, nullptr);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+int lgcn_launch_segsum_gn_relu(const float* a, const float* c, const int32_t* rowptr, const float* gamma,
+                               const float* beta, float* out, int64_t n_cap, const int32_t* n_dev, cudaStream_t st) {
+  if (n_cap <= 0) return 0;
+  k_gather_gn_relu<true><<<lgcn_cdiv(n_cap, GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(a, LGCN_C, c, rowptr, nullptr, gamma,
+                                                                                      beta, out, n_cap, n_dev);
   LGCN_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int lgcn_segsum_gn_relu(const float* a, const float* c, const int32_t* rowptr, const float* gamma,
                                    const float* beta, float* out, int64_t n_rows, void* stream) {
-  if (n_rows <= 0) return 0;
-  k_gather_gn_relu<true><<<lgcn_cdiv(n_rows, GATHER_WARPS), GATHER_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      a, LGCN_C, c, rowptr, nullptr, gamma, beta, out, n_rows);
-  LGCN_LAUNCH_OK();
-  return 0;
+  return lgcn_launch_segsum_gn_relu(a, c, rowptr, gamma, beta, out, n_rows, nullptr, (cudaStream_t)stream);
 }

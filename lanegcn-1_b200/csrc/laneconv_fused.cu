@@ -37,6 +37,7 @@
 // Measured (batch 128: 193,536 rows, 2.4 M edges): 0.48 ms per block against 0.81 ms for the three split kernels;
 // DESIGN.md section 3 lists what the tuning found and what was tried and rejected.
 #include <cstring>
+#include <mutex>
 
 #include "tc_common.cuh"
 
@@ -80,7 +81,8 @@ struct FusedArgs {
   const float* XA;       // auxiliary rows (multi-source sums)
   const int32_t* tab;    // [n_tiles][n_keys][128]
   const float* gn;       // gamma1 | beta1 | gamma2 | beta2
-  int64_t M;
+  int64_t M;             // row capacity (grid, tensor-map extent) ...
+  const int32_t* m_dev;  // ... and, when not NULL, the live row count in device memory (min(*m_dev, M) rows are processed)
   int n_keys;
   int chain;             // 1: ctr2 + GN + residual + ReLU inside the kernel
   // linear mode (tab == nullptr): out = epilogue( sum_k W_k . src[k][ idx[k] ? idx[k][row] : row ] ), the generic
@@ -148,7 +150,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const uint32_t tmem_base = *tmem_slot;
 
   // scalars only below (a by-value struct captured by reference in a lambda ends up in local memory)
-  const int64_t M = a.M;
+  const int64_t M = lgcn_devn(a.m_dev, a.M);
   const float* __restrict__ X = a.X;
   const float* __restrict__ XA = a.XA;
   const int32_t* __restrict__ tab = a.tab;
@@ -724,9 +726,11 @@ struct PlanHdr {
 };
 
 __global__ void k_plan_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_keys,
-                             int64_t n_nodes, int64_t n_rows_padded, int32_t* __restrict__ hdr,
+                             int64_t n_cap, const int32_t* __restrict__ n_dev, int32_t* __restrict__ hdr,
                              int32_t* __restrict__ tab, int2* __restrict__ mdesc, int32_t* __restrict__ mcol,
                              int64_t max_multi) {
+  const int64_t n_nodes = lgcn_devn(n_dev, n_cap);
+  const int64_t n_rows_padded = (n_nodes + kTileM - 1) / kTileM * kTileM;
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_rows_padded) return;
   int32_t* my = tab + ((m >> 7) * n_keys << 7) + (m & 127);
@@ -784,7 +788,6 @@ k_multi_sum(const float* __restrict__ X, const int32_t* __restrict__ hdr, const 
   }
 }
 
-bool g_attr_set = false;
 long long* g_timeline = nullptr;
 
 struct PlanView {
@@ -817,20 +820,25 @@ extern "C" int64_t lgcn_laneconv_plan_bytes(int64_t n_nodes, int64_t n_edges, in
          lgcn_align_up(n_edges * 4, 256) + 256;
 }
 
-extern "C" int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes,
-                                        int64_t n_edges, void* plan, void* stream) {
+// n_nodes / n_edges are capacities when n_dev (live node count in device memory) is given
+int lgcn_launch_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes, const int32_t* n_dev,
+                           int64_t n_edges, void* plan, cudaStream_t st) {
   LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= LGCN_MAX_KEYS, "plan_build: n_keys %d", n_keys);
   LGCN_CHECK_ARG(plan && (n_nodes == 0 || rowptr), "plan_build: NULL argument");
   LGCN_CHECK_ARG(n_nodes >= 0 && n_edges >= 0 && n_nodes < (1ll << 31) / 16, "plan_build: sizes");
-  cudaStream_t st = (cudaStream_t)stream;
   PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
   LGCN_CUDA_OK(cudaMemsetAsync(v.hdr, 0, 256, st));
   const int64_t rows = (n_nodes + kTileM - 1) / kTileM * kTileM;
   if (rows == 0 || n_keys == 0) return 0;
-  k_plan_build<<<lgcn_cdiv(rows, 256), 256, 0, st>>>(rowptr, col, n_keys, n_nodes, rows, v.hdr, v.tab, v.mdesc, v.mcol,
+  k_plan_build<<<lgcn_cdiv(rows, 256), 256, 0, st>>>(rowptr, col, n_keys, n_nodes, n_dev, v.hdr, v.tab, v.mdesc, v.mcol,
                                                     v.max_multi);
   LGCN_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int lgcn_laneconv_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys, int64_t n_nodes,
+                                        int64_t n_edges, void* plan, void* stream) {
+  return lgcn_launch_plan_build(rowptr, col, n_keys, n_nodes, nullptr, n_edges, plan, (cudaStream_t)stream);
 }
 
 // profiling aid (tools/timeline_fused.py): device buffer [1024][8] of clock64 stamps written by CTA 0 when debug flag
@@ -873,14 +881,29 @@ __global__ void k_split_many(const LgcnSplitList l, float* __restrict__ hi, floa
   reinterpret_cast<float4*>(lo)[i] = c;
 }
 
-// Scratch for the split weights of a launch: a ring of device slots, each guarded by an event recorded after the
-// kernel that read it, so a slot is never rewritten (on any stream) before its last reader has finished.
+// Scratch for the split weights of a launch whose caller did not pre-split them (the stand-alone lgcn_linear128 entry
+// point; lgcn_forward / lgcn_att_forward / the LaneConv stacks pass pre-split weights and never come here): a ring of
+// device slots PER DEVICE, each guarded by an event recorded after the kernel that read it, so a slot is never
+// rewritten (on any stream) before its last reader has finished.  The cursor is taken under a mutex (ctypes releases
+// the GIL, so two host threads may call concurrently).
 constexpr int kRing = 16;
 constexpr int64_t kSlotFloats = 2 * 3 * 128 * 128;
-float* g_ring = nullptr;
-cudaEvent_t g_ring_ev[kRing];
-bool g_ring_used[kRing];
-int g_ring_next = 0;
+struct SplitRing {
+  float* buf = nullptr;
+  cudaEvent_t ev[kRing];
+  bool used[kRing];
+  int next = 0;
+};
+SplitRing g_rings[kMaxDevices];
+std::mutex g_ring_mu;
+
+int set_fused_attrs() {
+  if (!first_use(kFamFused)) return 0;
+  LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  return 0;
+}
 }  // namespace
 
 int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st) {
@@ -894,26 +917,23 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   if (la.m <= 0) return 0;
   LGCN_CHECK_ARG(la.n_out_blocks == 1 && (la.ks == 0 || la.ks == 4) && la.n_src >= 1 && la.n_src <= 3,
                  "linear_fused: unsupported shape");
-  if (!g_attr_set) {
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    g_attr_set = true;
-  }
+  if (int rc = set_fused_attrs()) return rc;
   const float *w_hi = la.w_hi, *w_lo = la.w_lo;
   int slot = -1;
+  SplitRing& ring = g_rings[current_device()];
   if (!w_hi || !w_lo) {   // split W into a scratch slot
-    if (!g_ring) {
-      LGCN_CUDA_OK(cudaMalloc(&g_ring, kRing * kSlotFloats * sizeof(float)));
+    std::lock_guard<std::mutex> lock(g_ring_mu);
+    if (!ring.buf) {
+      LGCN_CUDA_OK(cudaMalloc(&ring.buf, kRing * kSlotFloats * sizeof(float)));
       for (int i = 0; i < kRing; ++i) {
-        LGCN_CUDA_OK(cudaEventCreateWithFlags(&g_ring_ev[i], cudaEventDisableTiming));
-        g_ring_used[i] = false;
+        LGCN_CUDA_OK(cudaEventCreateWithFlags(&ring.ev[i], cudaEventDisableTiming));
+        ring.used[i] = false;
       }
     }
-    slot = g_ring_next;
-    g_ring_next = (g_ring_next + 1) % kRing;
-    if (g_ring_used[slot]) LGCN_CUDA_OK(cudaStreamWaitEvent(st, g_ring_ev[slot], 0));
-    float* s_hi = g_ring + slot * kSlotFloats;
+    slot = ring.next;
+    ring.next = (ring.next + 1) % kRing;
+    if (ring.used[slot]) LGCN_CUDA_OK(cudaStreamWaitEvent(st, ring.ev[slot], 0));
+    float* s_hi = ring.buf + slot * kSlotFloats;
     float* s_lo = s_hi + kSlotFloats / 2;
     const int64_t ldw = (int64_t)la.n_src * LGCN_C + la.ks;
     k_split_blocks<<<lgcn_cdiv(la.n_src * 128 * 32, 256), 256, 0, st>>>(la.W, ldw, la.n_src, s_hi, s_lo);
@@ -940,15 +960,16 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
     a.wx = la.W + (int64_t)la.n_src * LGCN_C;
     a.ldw = (int64_t)la.n_src * LGCN_C + 4;
   }
-  a.flags = la.flags; a.M = la.m; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
+  a.flags = la.flags; a.M = la.m; a.m_dev = la.m_dev; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
   const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
   if (la.ks == 4) k_laneconv_fused<true, true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   else k_laneconv_fused<true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   LGCN_LAUNCH_OK();
   if (slot >= 0) {
-    LGCN_CUDA_OK(cudaEventRecord(g_ring_ev[slot], st));
-    g_ring_used[slot] = true;
+    std::lock_guard<std::mutex> lock(g_ring_mu);
+    LGCN_CUDA_OK(cudaEventRecord(ring.ev[slot], st));
+    ring.used[slot] = true;
   }
   return 0;
 }
@@ -957,17 +978,12 @@ int64_t lgcn_laneconv_fused_aux_bytes(int64_t n_edges) { return lgcn_align_up((n
 
 // out[m] = one LaneConv block of x (chain = 1) or relu(GN(sum_k W_k agg_k)) (chain = 0).  w_hi / w_lo: pre-split
 // [(n_keys + 1 (+1 with chain: ctr2)) * 128, 128]; gn: gamma1 | beta1 | gamma2 | beta2; xa: aux rows workspace.
-int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, int64_t n_edges, int n_keys,
-                               const float* w_hi, const float* w_lo, const float* gn, float* xa, int chain,
-                               cudaStream_t st) {
+int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, const int32_t* n_dev,
+                               int64_t n_edges, int n_keys, const float* w_hi, const float* w_lo, const float* gn,
+                               float* xa, int chain, cudaStream_t st) {
   if (n_nodes <= 0) return 0;
   LGCN_CHECK_ARG(x != out, "laneconv_fused: in-place is not possible (neighbour rows are read by other tiles)");
-  if (!g_attr_set) {
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    g_attr_set = true;
-  }
+  if (int rc = set_fused_attrs()) return rc;
   PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
   if (n_keys > 0 && n_edges > 1) {
     k_multi_sum<<<num_sms() * 4, 256, 0, st>>>(x, v.hdr, v.mdesc, v.mcol, xa, v.max_multi);
@@ -980,7 +996,7 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
   FusedArgs a;
   memset(&a, 0, sizeof(a));
-  a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.n_keys = n_keys; a.chain = chain; a.dbg = lgcn_debug_get();
+  a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.m_dev = n_dev; a.n_keys = n_keys; a.chain = chain; a.dbg = lgcn_debug_get();
   a.tl = g_timeline;
   const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());

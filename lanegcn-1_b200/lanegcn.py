@@ -22,6 +22,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _C
+from . import forward_engine as FE
 from .blocks import ActorNet, Linear, PredNet
 
 # --------------------------------------------------------------------------- config (lanegcn.py:28-92)
@@ -39,6 +40,7 @@ KEEP_PAIR_QUIRK = True  # reproduce the reference's empty-scene offset behaviour
 # LaneConv blocks: True = aggregate-first single kernel (laneconv_fused.cu), False = wide projection + CSR gather +
 # ctr2 (gemm_tc_wide.cu, laneconv.cu).  LGCN_LANECONV=split selects the latter.
 LANECONV_FUSED = os.environ.get("LGCN_LANECONV", "fused") != "split"
+MAX_BUCKETS = 8         # capacity buckets (static buffers + CUDA graphs) a Net keeps alive; oldest evicted first
 
 
 # --------------------------------------------------------------------------- small host-side helpers
@@ -156,12 +158,15 @@ class _WPack:
     ``refs`` (a callable returning ``[(module, parameter_name), ...]``) is evaluated once: walking the module tree
     through ``nn.Module.__getattr__`` for ~260 parameters cost 0.3 ms of host time per forward.  Every call still
     reads the CURRENT parameter objects from the owning modules' ``_parameters`` dicts, so replaced, re-assigned or
-    in-place updated parameters are seen; only swapping a whole sub-module after the first forward is not."""
+    in-place updated parameters are seen; only swapping a whole sub-module after the first forward is not, and writes
+    through ``p.data`` (which do not bump ``_version``) need ``Net.invalidate_packs()``.  The buffer is refreshed IN
+    PLACE, so pointers captured in CUDA graphs stay valid."""
 
     def __init__(self):
         self.key = None
         self.buf = None
         self.refs = None
+        self.version = 0
 
     def get(self, refs) -> Tensor:
         if self.refs is None:
@@ -170,9 +175,19 @@ class _WPack:
         key = tuple([(t.data_ptr(), t._version) for t in tensors])
         if key != self.key:
             with torch.no_grad():
-                self.buf = torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
+                flat = [t.detach().reshape(-1).float() for t in tensors]
+                n = sum(f.numel() for f in flat)
+                if self.buf is not None and self.buf.numel() == n and self.buf.device == flat[0].device:
+                    torch.cat(flat, out=self.buf)   # in place: captured CUDA graphs hold this address
+                else:
+                    self.buf = torch.cat(flat).contiguous()
             self.key = key
+            self.version += 1
         return self.buf
+
+    def invalidate(self):
+        """Force a re-pack at the next use (for writes the version counter cannot see: ``p.data.copy_()``)."""
+        self.key = None
 
 
 # --------------------------------------------------------------------------- device-side graph container
@@ -315,10 +330,16 @@ def dilated_nbrs(nbr: Dict, num_nodes: int, num_scales: int, device=None) -> Lis
 
 # --------------------------------------------------------------------------- actor_gather / graph_gather
 def actor_gather(actors: List[Tensor]):
-    """lanegcn.py:155-168 — list of [A_i,20,3] -> ([sum A,3,20], per-scene index lists)."""
+    """lanegcn.py:155-168 — list of [A_i,20,3] -> ([sum A,3,20], per-scene index lists).  Host lists are staged
+    through one pinned buffer (one H2D copy); the transpose is a kernel (lgcn_actor_gather)."""
     sizes = [len(x) for x in actors]
-    cat = torch.cat(list(actors), 0).transpose(1, 2).contiguous()
-    idcs = scene_list(torch.arange(sum(sizes), device=cat.device), sizes)
+    dev = _target_device(actors[0])
+    flat = _stage_cat(list(actors), dev, torch.float32, "actor_gather")[0]
+    n, (t, c) = sum(sizes), tuple(actors[0].shape[1:])
+    cat = torch.empty(n, c, t, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().lgcn_actor_gather(flat.data_ptr(), cat.data_ptr(), n, t, c, _C.stream_ptr()), "actor_gather")
+    idcs = scene_list(torch.arange(n, device=dev), sizes)
     return cat, idcs
 
 
@@ -515,11 +536,44 @@ def _stage(t: Tensor, dev, dtype, tag: str = "misc") -> Tensor:
     return _stage_cat([t.reshape(-1)], dev, dtype, tag + str(dtype))[0].view(shape)
 
 
+_PENDING_PINNED: List = []
+
+
+def _pack_pinned(parts: List[Tensor], dtype, tag: str) -> Tensor:
+    """Concatenate CPU tensors (flattened, in order) into a pinned staging buffer with the C packer and return the flat
+    HOST tensor; the caller issues its own H2D copies from it and then calls ``_release_pinned`` (which ties the
+    buffer's reuse to those copies)."""
+    if set(map(_DTYPE, parts)) != {dtype} or not all(map(_IS_CONTIG, parts)):
+        parts = [p.to(dtype).contiguous() for p in parts]
+    k = len(parts)
+    sizes = np.array(list(map(_NBYTES, parts)), np.int64)
+    ptrs = np.array(list(map(_DATA_PTR, parts)), np.uint64)
+    nbytes = int(sizes.sum())
+    ring, i, buf = _PinnedPool.take(tag, nbytes)
+    if nbytes:
+        _C.check(_C.lib().lgcn_pack_host(ptrs.ctypes.data, sizes.ctypes.data, k, buf.data_ptr(), nbytes, _PACK_THREADS),
+                 "pack_host")
+    _PENDING_PINNED.append((ring, i))
+    return buf[:nbytes].view(dtype)
+
+
+def _release_pinned():
+    """One event on the current stream after the H2D copies that read the pinned buffers taken since the last call."""
+    if _PENDING_PINNED:
+        ev = torch.cuda.Event()
+        ev.record()
+        for ring, i in _PENDING_PINNED:
+            ring["evs"][i] = ev
+        _PENDING_PINNED.clear()
+
+
 # --------------------------------------------------------------------------- Att pair lists
 class PairList:
     """hi/wi (int32) + destination rowptr for one (agents, contexts, threshold) triple."""
 
     def __init__(self, agt: SceneList, ctx: SceneList, th: float):
+        if len(agt) != len(ctx):
+            raise RuntimeError(f"lanegcn_b200: {len(agt)} agent scenes but {len(ctx)} context scenes")
         self.agt, self.ctx, self.th = agt, ctx, float(th)
         self.n_agt, self.n_ctx = int(agt.cat.shape[0]), int(ctx.cat.shape[0])
         dev = agt.cat.device
@@ -559,18 +613,23 @@ def count_pair_lists(specs) -> List[PairList]:
     return pls
 
 
-def fill_pair_lists(pls: List[PairList], want_int64: bool = False, counted: "torch.cuda.Event" = None) -> List[PairList]:
+def fill_pair_lists(pls: List[PairList], want_int64: bool = False, counted: "torch.cuda.Event" = None,
+                    err: Optional[Tensor] = None) -> List[PairList]:
     """Read the pair totals (ONE device->host synchronisation for all lists) and enqueue the fill kernels.
     With ``counted`` (an event recorded right after the count kernels) the read-back runs on an auxiliary stream
     that waits for that event only, so work enqueued on the main stream in the meantime keeps the device busy
-    and the host does not wait for it."""
+    and the host does not wait for it.  ``err`` (the CSR builder's error flag) rides along in the same transfer:
+    an out-of-range edge index raises here, like the reference's index_add_ would."""
+    words = [p.rowptr[-1] for p in pls] + ([err[0]] if err is not None else [])
     if counted is None:
-        totals = torch.stack([p.rowptr[-1] for p in pls]).tolist()  # the one D2H sync
+        totals = torch.stack(words).tolist()  # the one D2H sync
     else:
         aux = _side_stream(pls[0].rowptr.device, "aux")
         aux.wait_event(counted)
         with torch.cuda.stream(aux):
-            totals = torch.stack([p.rowptr[-1] for p in pls]).tolist()
+            totals = torch.stack(words).tolist()
+    if err is not None and totals[-1]:
+        raise RuntimeError("lanegcn_b200: graph edge index out of range [0, num_nodes)")
     for p, n in zip(pls, totals):
         p.fill(n, want_int64)
     return pls
@@ -883,17 +942,40 @@ class DeviceBatch:
     def __init__(self):
         self.actors = None       # f32 [sum A, 20, 3] (transposed on the device)
         self.actor_ctrs = None   # SceneList over f32 [sum A, 2]
-        self.graphs = None       # StagedGraphs
+        self.graphs = None       # StagedGraphs (module path only)
         self.rot = None          # f32 [B,2,2]
         self.orig = None         # f32 [B,2]
         self.ready = None        # event: the staging copies (issued on the copy stream) have completed
-        self.rot_a = None        # f32 [sum A,2,2]  the scene's rot, per actor
+        self.rot_a = None        # f32 [sum A,2,2]  the scene's rot, per actor (module path only)
         self.orig_a = None       # f32 [sum A,2]
         self.h2d_bytes = 0
+        self.slot = None         # forward_engine.Slot: the static buffers this batch was staged into (one-call path)
+        self.sizes = None        # actors per scene
+        self.n_nodes = 0
+        self.n_actors = 0
+        self.data = None         # the collated host batch (kept so that a pair-capacity overflow can be re-run)
+        self.checked = None      # result of Net.check for this batch (None: not read yet)
+
+
+class _ForwardWeights:
+    """The weight packs lgcn_forward reads + their tf32 images (refreshed in place when a parameter changes)."""
+
+    def __init__(self):
+        self.packs = {k: _WPack() for k in ("map_input", "map_seg", "a2m_meta")}
+        self.prepared = None
+        self.struct = _C.ForwardWeights()
+        self.key = None
 
 
 class Net(nn.Module):
-    """LaneGCN (lanegcn.py:94-151): ActorNet, MapNet, A2M -> M2M -> M2A -> A2A, PredNet."""
+    """LaneGCN (lanegcn.py:94-151): ActorNet, MapNet, A2M -> M2M -> M2A -> A2A, PredNet.
+
+    Two execution paths with identical results:
+      * the ONE-CALL path (default; tcgen05 engine + aggregate-first LaneConv): ``stage`` packs the batch into the
+        static buffers of a capacity bucket, ``forward_device`` replays one CUDA graph (ActorNet | lgcn_forward |
+        PredNet + world transform) — no host synchronisation, a handful of host calls per batch;
+      * the MODULE path (other engines, inputs already on the GPU, LGCN_FORWARD=modules): the drop-in modules called
+        one after the other like the reference's Net.forward, with one host synchronisation for the pair totals."""
 
     def __init__(self, config):
         super().__init__()
@@ -905,9 +987,12 @@ class Net(nn.Module):
         self.m2a = M2A(config)
         self.a2a = A2A(config)
         self.pred_net = PredNet(config)
-        self.use_cuda_graphs = os.environ.get("LGCN_NO_GRAPHS", "0") != "1"  # ActorNet / PredNet only
+        self.use_cuda_graphs = os.environ.get("LGCN_NO_GRAPHS", "0") != "1"
         self._g_actor = _Graphed(self.actor_net)
         self._g_pred = _Graphed(self._pred_core)
+        self._buckets: Dict = {}
+        self._pair_learned: Optional[List[int]] = None
+        self._fw: Dict = {}
 
     def _pred_core(self, actors, ctrs, rot_a, orig_a):
         """PredNet + the world transform of lanegcn.py:145-150, per actor row (graph-capturable)."""
@@ -920,20 +1005,172 @@ class Net(nn.Module):
             raise RuntimeError("lanegcn_b200: move the model to a CUDA device first (there is no CPU path)")
         return dev
 
+    def one_call_path(self) -> bool:
+        return (LANECONV_FUSED and _C.lib().lgcn_get_gemm_engine() == 1
+                and os.environ.get("LGCN_FORWARD", "onecall") != "modules")
+
+    def invalidate_packs(self):
+        """Re-pack every weight copy at the next forward (needed only after writes through ``p.data``)."""
+        for m in self.modules():
+            wp = getattr(m, "_wp", None)
+            if isinstance(wp, _WPack):
+                wp.invalidate()
+        for fw in self._fw.values():
+            for wp in fw.packs.values():
+                wp.invalidate()
+
+    # ------------------------------------------------------------------ weights of the one-call path
+    def _weights(self, dev) -> _ForwardWeights:
+        fw = self._fw.get(str(dev))
+        if fw is None:
+            fw = self._fw[str(dev)] = _ForwardWeights()
+        mn, lib = self.map_net, _C.lib()
+        mlp = lambda seq: (lambda: [(seq[0], "weight"), (seq[0], "bias"), (seq[2].linear, "weight"),  # noqa: E731
+                                    (seq[2].norm, "weight"), (seq[2].norm, "bias")])
+        packs = [fw.packs["map_input"].get(mlp(mn.input)), fw.packs["map_seg"].get(mlp(mn.seg)), mn._wpack(),
+                 fw.packs["a2m_meta"].get(lambda: [(self.a2m.meta.linear, "weight"), (self.a2m.meta.norm, "weight"),
+                                                    (self.a2m.meta.norm, "bias")])]
+        atts = [att._wpack() for att in list(self.a2m.att) + list(self.m2a.att) + list(self.a2a.att)]
+        m2m = self.m2m._wpack()
+        wps = [fw.packs["map_input"], fw.packs["map_seg"], mn._wp, fw.packs["a2m_meta"], self.m2m._wp] + \
+              [att._wp for att in list(self.a2m.att) + list(self.m2a.att) + list(self.a2a.att)]
+        key = tuple((w.buf.data_ptr(), w.version) for w in wps)
+        if key != fw.key:
+            st = fw.struct
+            st.map_input, st.map_seg, st.map_fuse, st.a2m_meta = (t.data_ptr() for t in packs)
+            st.att = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in atts])
+            st.m2m_fuse = m2m.data_ptr()
+            nbytes = lib.lgcn_forward_prepared_bytes(self.config["num_scales"])
+            if fw.prepared is None or fw.prepared.device != dev or fw.prepared.numel() != nbytes:
+                fw.prepared = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            st.prepared = fw.prepared.data_ptr()
+            _C.check(lib.lgcn_forward_prepare(ctypes.byref(st), self.config["num_scales"], _C.stream_ptr()), "forward_prepare")
+            fw.key = key
+        return fw
+
+    # ------------------------------------------------------------------ staging
     def stage(self, data: Dict) -> DeviceBatch:
         """Host packing + H2D of one collated batch (what utils.gpu does tensor by tensor, utils.py:74-85): every
         float of the batch travels in ONE pinned arena, the edge indices in a second, two small integer tables."""
+        if self.one_call_path() and not data["feats"][0].is_cuda and sum(len(x) for x in data["feats"]) > 0 \
+                and sum(int(g["num_nodes"]) for g in data["graph"]) > 0:
+            return self._stage_slot(data)
+        return self._stage_modules(data)
+
+    def _stage_slot(self, data: Dict) -> DeviceBatch:
+        dev = self._device()
+        graphs = data["graph"]
+        B = len(graphs)
+        node_sizes = [int(g["num_nodes"]) for g in graphs]
+        sizes = [len(x) for x in data["feats"]]
+        N, A = sum(node_sizes), sum(sizes)
+        S = len(graphs[0]["pre"])
+        names = _edge_names(S)
+        locs = []
+        for k1, sc in names:
+            src = [g[k1] for g in graphs] if sc is None else [g[k1][sc] for g in graphs]
+            for k2 in ("u", "v"):
+                locs += [d[k2] for d in src]
+        if any(t.dim() == 0 for t in locs[-4 * B:]):  # pickles where an empty left/right array collapsed to a scalar
+            locs = [t.new_zeros(0) if t.dim() == 0 else t for t in locs]                   # (lanegcn.py:204-207)
+        dt = locs[0].dtype
+        if set(map(_DTYPE, locs)) != {dt}:
+            dt, locs = torch.int64, [t.long() for t in locs]
+        if dt not in (torch.int16, torch.int32, torch.int64):
+            raise RuntimeError(f"lanegcn_b200: edge indices must be int16/int32/int64, got {dt}")
+        if not all(map(_IS_CONTIG, locs)):
+            locs = [t.contiguous() for t in locs]
+        isz = locs[0].element_size()
+        seg_len = np.array(list(map(_NBYTES, locs)), np.int64) // isz
+        total = int(seg_len.sum())
+        cap_a = FE.round_cap(A)
+        caps = FE.Caps((FE.round_cap(N, 128), cap_a, FE.round_cap(total + (total & 1), 1024), FE.round_cap(B, 1),
+                        *FE.pair_caps(node_sizes, sizes, self._pair_learned, cap_a), isz, S))
+        bucket = self._buckets.get((str(dev), caps))
+        if bucket is None:
+            while len(self._buckets) >= MAX_BUCKETS:           # oldest first (dicts keep insertion order)
+                self._buckets.pop(next(iter(self._buckets)))
+            with torch.cuda.device(dev):
+                bucket = self._buckets[(str(dev), caps)] = FE.Bucket(caps, dev, self.config, KEEP_PAIR_QUIRK)
+        slot = bucket.next_slot()
+        Bc = caps.scenes
+        b = DeviceBatch()
+        b.slot, b.sizes, b.n_nodes, b.n_actors, b.data = slot, sizes, N, A, data
+        with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev, "copy")):
+            copy = torch.cuda.current_stream()
+            if slot.done is not None:
+                copy.wait_event(slot.done)       # the previous forward on this slot has read its inputs
+            # ---- floats: [ctrs | feats | turn | control | intersect | actor feats | actor ctrs | rot | orig]
+            parts = []
+            for key in ("ctrs", "feats", "turn", "control", "intersect"):
+                parts += [g[key] for g in graphs]
+            parts += list(data["feats"]) + list(data["ctrs"]) + list(data["rot"]) + list(data["orig"])
+            host_fl = _pack_pinned(parts, torch.float32, "slot_fl")
+            reg_sizes = [2 * N, 2 * N, 2 * N, N, N, 60 * A, 2 * A, 4 * B, 2 * B]
+            if host_fl.numel() != sum(reg_sizes):
+                raise RuntimeError("lanegcn_b200: unexpected per-scene tensor shapes in the batch")
+            src, runs = 0, []   # (dst offset, src offset, length), adjacent regions merged
+            for r, n in enumerate(reg_sizes):
+                if runs and runs[-1][0] + runs[-1][2] == slot.fl_off[r]:
+                    runs[-1][2] += n
+                elif n:
+                    runs.append([slot.fl_off[r], src, n])
+                src += n
+            for dst, so, n in runs:
+                slot.fl[dst: dst + n].copy_(host_fl[so: so + n], non_blocking=True)
+            # ---- scene-local edge indices, back to back in output order
+            host_idx = _pack_pinned(locs, dt, "slot_idx")
+            if total:
+                slot.local[:total].copy_(host_idx, non_blocking=True)
+            # ---- tables at capacity: segments of absent scene slots are empty
+            n_kv = 2 * len(names)
+            lens = np.zeros((n_kv, Bc), np.int64)
+            lens[:, :B] = seg_len.reshape(n_kv, B)
+            t64 = np.empty(2 * n_kv * Bc + 1, np.int64)
+            t64[0] = 0
+            np.cumsum(lens.reshape(-1), out=t64[1: n_kv * Bc + 1])
+            noff = np.full(Bc + 1, N, np.int64)
+            noff[: B + 1] = np.concatenate(([0], np.cumsum(node_sizes)))
+            t64[n_kv * Bc + 1:] = np.tile(noff[:-1], n_kv)
+            aoff = np.full(Bc + 1, A, np.int64)
+            aoff[: B + 1] = np.concatenate(([0], np.cumsum(sizes)))
+            t32 = np.concatenate((noff, aoff, [N, A, 0, 0])).astype(np.int32)
+            h64 = _pack_pinned([torch.from_numpy(t64)], torch.int64, "slot_t64")
+            h32 = _pack_pinned([torch.from_numpy(t32)], torch.int32, "slot_t32")
+            slot.t64.copy_(h64, non_blocking=True)
+            slot.t32.copy_(h32, non_blocking=True)
+            _release_pinned()
+            b.h2d_bytes = 4 * host_fl.numel() + isz * total + 8 * h64.numel() + 4 * h32.numel()
+            b.ready = torch.cuda.Event()
+            b.ready.record()
+        b.actor_ctrs = scene_list(slot.actor_ctrs[:A], sizes, slot.actor_off[: B + 1], lazy=True)
+        return b
+
+    def _stage_modules(self, data: Dict) -> DeviceBatch:
         dev = self._device()
         # everything below runs on a dedicated copy stream, so the H2D transfers of batch i+1 overlap the kernels
         # of batch i (prefetch_forward); forward_device waits for b.ready before touching the staged tensors
+        cur0 = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev, "copy")):
             b = DeviceBatch()
+            b.data = data
             sizes = [len(x) for x in data["feats"]]
+            b.sizes = sizes
             A, B = sum(sizes), len(sizes)
             aoff = [0]
             for n in sizes:
                 aoff.append(aoff[-1] + n)
             if data["feats"][0].is_cuda:  # already on the device: no staging to do for the actor side
+                # the caller's tensors were produced on ITS stream: order the copy stream behind it and keep the
+                # sources alive until the copy stream has read them
+                copy = torch.cuda.current_stream()
+                copy.wait_stream(cur0)
+                for t in list(data["feats"]) + list(data["ctrs"]) + list(data["rot"]) + list(data["orig"]):
+                    t.record_stream(copy)
+                for g in data["graph"]:
+                    for t in _graph_tensors(g):
+                        if t.is_cuda:
+                            t.record_stream(copy)
                 sg = stage_graphs(data["graph"])
                 b.actors = torch.cat(list(data["feats"]), 0).float()
                 ctrs = torch.cat(list(data["ctrs"]), 0).float()
@@ -953,18 +1190,135 @@ class Net(nn.Module):
             b.rot_a = torch.repeat_interleave(b.rot, cnt, 0, output_size=A)     # the scene's rot / orig per actor
             b.orig_a = torch.repeat_interleave(b.orig, cnt, 0, output_size=A)
             b.graphs = sg
+            b.n_nodes, b.n_actors = sg.off[-1], A
             b.h2d_bytes = sg.h2d_bytes
             b.ready = torch.cuda.Event()
             b.ready.record()
             return b
 
+    # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, data: Dict) -> Dict[str, List[Tensor]]:
-        out = self.forward_device(self.stage(data))
+        b = self.stage(data)
+        out = self.forward_device(b)
+        if b.slot is not None:
+            if self.check(b):                      # a pair list did not fit its capacity: rerun with the exact counts
+                b = self.stage(data)
+                out = self.forward_device(b)
+                if self.check(b):
+                    raise RuntimeError("lanegcn_b200: pair capacity overflow after growing (internal error)")
+            out = {k: scene_list(v.cat.clone(), v.sizes, v.off_dev, lazy=True) for k, v in out.items()}
         return {k: v.materialize() if isinstance(v, SceneList) else v for k, v in out.items()}
 
     @torch.no_grad()
-    def forward_device(self, b: DeviceBatch) -> Dict[str, List[Tensor]]:
+    def forward_taps(self, data: Dict, taps: Dict[str, Tensor]) -> Dict[str, List[Tensor]]:
+        """``forward`` that also records the output of every stage (actor_net, map_net, a2m, m2m, m2a, a2a) in
+        ``taps`` — the hooks the parity tests compare with the oracle's."""
+        b = self.stage(data)
+        out = self.forward_device(b, taps)
+        if b.slot is not None:
+            if self.check(b):
+                taps.clear()
+                b = self.stage(data)
+                out = self.forward_device(b, taps)
+                self.check(b)
+            out = {k: scene_list(v.cat.clone(), v.sizes, v.off_dev, lazy=True) for k, v in out.items()}
+        return {k: v.materialize() if isinstance(v, SceneList) else v for k, v in out.items()}
+
+    def check(self, b: DeviceBatch) -> bool:
+        """Read the status words of a batch run on the one-call path (SYNCHRONISES on that batch).  Returns True if a
+        pair list overflowed its capacity (the results of that batch are invalid: run it again, the capacities have
+        been raised); raises like the reference does when a list is empty (lanegcn.py:688) or an index is bad."""
+        if b.slot is None:
+            return False
+        if b.checked is None:
+            b.slot.status_ev.synchronize()
+            st = b.slot.status_host.tolist()
+            seen = st[1:4]
+            self._pair_learned = seen if self._pair_learned is None else [max(x, y) for x, y in zip(seen, self._pair_learned)]
+            if st[4]:
+                raise RuntimeError("lanegcn_b200: graph edge index out of range [0, num_nodes)")
+            if st[0] & FE.ST_EMPTY:
+                raise RuntimeError("lanegcn_b200: Att found no agent/context pair within dist_th in any scene "
+                                   "(the reference raises here too: torch.cat of an empty list, lanegcn.py:688)")
+            b.checked = bool(st[0] & FE.ST_OVERFLOW)
+        return b.checked
+
+    def _run_slot(self, slot, fw: _ForwardWeights, n_nodes: int, n_actors: int, taps: Optional[Dict] = None):
+        """ActorNet | graph build + MapNet  ->  A2M, M2M, M2A, A2A (lgcn_forward)  ->  PredNet + world transform, on the
+        slot's static buffers: the sequence a CUDA graph of the bucket captures."""
+        lib, a, dev = _C.lib(), slot.args, slot.dev
+        a.w = fw.struct
+        cur, side = torch.cuda.current_stream(), _side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):   # ActorNet is independent of the map: a parallel branch
+            _C.check(lib.lgcn_actor_gather(slot.actor_feats.data_ptr(), slot.actors_t.data_ptr(), slot.caps.actors, 20, 3,
+                                           side.cuda_stream), "actor_gather")
+            slot.actors.copy_(self.actor_net(slot.actors_t))                                  # lanegcn.py:129-131
+
+        def run(stages):
+            a.stages = stages
+            _C.check(lib.lgcn_forward(ctypes.byref(a), cur.cuda_stream), "forward")
+
+        run(_C.STAGE_GRAPH | _C.STAGE_MAPNET)                                                 # :134-135
+        cur.wait_stream(side)
+        if taps is None:
+            run(_C.STAGE_A2M | _C.STAGE_M2M | _C.STAGE_M2A | _C.STAGE_A2A)                    # :138-141
+        else:
+            taps["actor_net"] = slot.actors[:n_actors].clone()
+            taps["map_net"] = slot.nodes[:n_nodes].clone()
+            for name, stage, buf, n in (("a2m", _C.STAGE_A2M, slot.nodes, n_nodes), ("m2m", _C.STAGE_M2M, slot.nodes, n_nodes),
+                                        ("m2a", _C.STAGE_M2A, slot.actors, n_actors), ("a2a", _C.STAGE_A2A, slot.actors, n_actors)):
+                run(stage)
+                taps[name] = buf[:n].clone()
+        cls, reg = self.pred_net.core(slot.actors, slot.actor_ctrs)                           # :144
+        slot.cls.copy_(cls)
+        slot.reg.copy_(reg)
+        _C.check(lib.lgcn_world_transform(slot.reg.data_ptr(), slot.actor_off.data_ptr(), slot.caps.scenes,
+                                          slot.rot.data_ptr(), slot.orig.data_ptr(), slot.caps.actors,
+                                          slot.dims[1:].data_ptr(), slot.reg.shape[1] * slot.reg.shape[2],
+                                          cur.cuda_stream), "world_transform")                # :145-150
+
+    @torch.no_grad()
+    def forward_device(self, b: DeviceBatch, taps: Optional[Dict] = None) -> Dict[str, List[Tensor]]:
+        """The forward from staged inputs.  On the one-call path the returned lists are VIEWS of the slot's static
+        output buffers: valid until the slot is staged again (two batches later); ``Net.forward`` returns copies."""
+        if b.slot is None:
+            return self._forward_modules(b, taps)
+        slot, dev, lib = b.slot, b.slot.dev, _C.lib()
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(b.ready)
+            if slot.d2h_done is not None:
+                cur.wait_event(slot.d2h_done)     # the previous results of this slot have been read back
+            fw = self._weights(dev)
+            if taps is None and self.use_cuda_graphs:
+                if slot.graph is None or slot.weights_version != fw.key:
+                    self._run_slot(slot, fw, b.n_nodes, b.n_actors)      # warm-up: lazy initialisation outside capture
+                    torch.cuda.synchronize(dev)
+                    n0 = lib.lgcn_launch_count()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run_slot(slot, fw, b.n_nodes, b.n_actors)
+                    slot.graph, slot.weights_version = g, fw.key
+                    slot.graph_kernels = int(lib.lgcn_launch_count() - n0)
+                slot.graph.replay()
+                self.replayed_kernels = getattr(self, "replayed_kernels", 0) + slot.graph_kernels
+            else:
+                self._run_slot(slot, fw, b.n_nodes, b.n_actors, taps)
+            slot.done = torch.cuda.Event()
+            slot.done.record(cur)
+            slot.status_host.copy_(slot.status, non_blocking=True)
+            slot.status_ev = torch.cuda.Event()
+            slot.status_ev.record(cur)
+            slot.d2h_done = slot.status_ev
+            A, B = b.n_actors, len(b.sizes)
+            off = slot.actor_off[: B + 1]
+            return {"cls": scene_list(slot.cls[:A], b.sizes, off, lazy=True),
+                    "reg": scene_list(slot.reg[:A], b.sizes, off, lazy=True)}
+
+    @torch.no_grad()
+    def _forward_modules(self, b: DeviceBatch, taps: Optional[Dict] = None) -> Dict[str, List[Tensor]]:
         cfg = self.config
         with torch.cuda.device(b.actors.device):
             cur = torch.cuda.current_stream()
@@ -997,15 +1351,25 @@ class Net(nn.Module):
             counted = torch.cuda.Event()
             counted.record(cur)
             nodes, node_idcs, node_ctrs = self.map_net(graph)                     # :135
-            # ... and only now take the ONE host synchronisation of the forward (three pair totals), on an auxiliary
-            # stream that waits for the count kernels only: the device stays busy with MapNet meanwhile.
-            p_a2m, p_m2a, p_a2a = fill_pair_lists(pls, counted=counted)
+            # ... and only now take the ONE host synchronisation of the forward (three pair totals + the CSR error
+            # flag), on an auxiliary stream that waits for the count kernels only: the device stays busy with MapNet.
+            p_a2m, p_m2a, p_a2a = fill_pair_lists(pls, counted=counted, err=graph["_packed"].err)
             cur.wait_stream(side)
             actors.record_stream(cur)
+            if taps is not None:
+                taps["actor_net"], taps["map_net"] = actors.clone(), nodes.clone()
             nodes = self.a2m(nodes, graph, actors, actor_idcs, actor_ctrs, pairs=p_a2m)   # :138
+            if taps is not None:
+                taps["a2m"] = nodes.clone()
             nodes = self.m2m(nodes, graph)                                        # :139
+            if taps is not None:
+                taps["m2m"] = nodes.clone()
             actors = self.m2a(actors, actor_idcs, actor_ctrs, nodes, node_idcs, node_ctrs, pairs=p_m2a)  # :140
+            if taps is not None:
+                taps["m2a"] = actors.clone()
             actors = self.a2a(actors, actor_idcs, actor_ctrs, pairs=p_a2a)        # :141
+            if taps is not None:
+                taps["a2a"] = actors.clone()
             # PredNet + world transform (:144-150), batched over actors
             if self.use_cuda_graphs:
                 cls, reg = self._g_pred(actors, actor_ctrs.cat, b.rot_a, b.orig_a)
@@ -1016,6 +1380,18 @@ class Net(nn.Module):
             # before returning, the throughput paths read ``.cat``)
             return {"cls": scene_list(cls, sizes, actor_ctrs.off_dev, lazy=True),
                     "reg": scene_list(reg, sizes, actor_ctrs.off_dev, lazy=True)}
+
+
+def _graph_tensors(g: dict):
+    for k, v in g.items():
+        if torch.is_tensor(v):
+            yield v
+        elif isinstance(v, dict):
+            yield from (t for t in v.values() if torch.is_tensor(t))
+        elif isinstance(v, list):
+            for e in v:
+                if isinstance(e, dict):
+                    yield from (t for t in e.values() if torch.is_tensor(t))
 
 
 def _cat_of(lst) -> Tensor:
@@ -1036,15 +1412,33 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
     deeper: the D2H copy of batch i is queued on its own stream behind an event, batch i+1 is launched, and only then
     is batch i handed out, so the device never waits for the host to read a result and relaunch.  ``post`` (optional)
     maps the device outputs of a batch to the dict that is handed out / copied, on the compute stream right after the
-    forward (the multi-GPU result gather, ``shard.gather_outputs``)."""
+    forward (the multi-GPU result gather, ``shard.gather_outputs``).
+
+    A batch whose pair lists overflowed their capacity (one-call path; ``Net.check``) is recomputed with
+    ``Net.forward`` before it is handed out."""
     it = iter(batches)
     try:
         staged = net.stage(next(it))
     except StopIteration:
         return
-    held = None   # (cls_host, reg_host, sizes, copied event) of the previous batch
+
+    def redo(b):   # capacity overflow: the capacities have been raised by Net.check, run the batch again
+        out = net.forward(b.data)
+        if post is not None:
+            out = post(out)
+        return out
+
+    def hand_out(h):
+        cls_h, reg_h, sizes, copied, b = h
+        copied.synchronize()
+        if net.check(b):
+            out = redo(b)
+            return {k: [t.cpu() for t in out[k]] for k in ("cls", "reg")}
+        return {"cls": list(cls_h.split_with_sizes(sizes)), "reg": list(reg_h.split_with_sizes(sizes))}
+
+    held = None   # (cls_host, reg_host, sizes, copied event, batch) of the previous batch
     while staged is not None:
-        out = net.forward_device(staged)          # enqueued; the host returns after the one pair-count sync
+        out = net.forward_device(staged)          # enqueued; no host synchronisation on the one-call path
         if post is not None:
             out = post(out)
         if to_host:
@@ -1063,7 +1457,14 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
                     reg_d.record_stream(d2h)
                     copied = torch.cuda.Event()
                     copied.record(d2h)
-            mine = (cls_h, reg_h, sizes, copied)
+                if staged.slot is not None and post is None:
+                    staged.slot.d2h_done = copied   # the slot's static outputs may be overwritten after this
+            mine = (cls_h, reg_h, sizes, copied, staged)
+        elif staged.slot is not None:
+            if net.check(staged):
+                out = redo(staged)
+            elif post is None:   # views of the slot's static buffers -> private copies
+                out = {k: scene_list(v.cat.clone(), v.sizes, v.off_dev, lazy=True) for k, v in out.items()}
         try:
             nxt = net.stage(next(it))             # host packing + H2D of the next batch while the GPU computes
         except StopIteration:
@@ -1072,13 +1473,11 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
             yield {k: v.materialize() if isinstance(v, SceneList) else v for k, v in out.items()}
         else:
             if held is not None:
-                held[3].synchronize()
-                yield {"cls": list(held[0].split_with_sizes(held[2])), "reg": list(held[1].split_with_sizes(held[2]))}
+                yield hand_out(held)
             held = mine
         staged = nxt
     if to_host and held is not None:
-        held[3].synchronize()
-        yield {"cls": list(held[0].split_with_sizes(held[2])), "reg": list(held[1].split_with_sizes(held[2]))}
+        yield hand_out(held)
 
 
 def get_model():
