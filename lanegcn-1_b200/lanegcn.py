@@ -1412,7 +1412,8 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
     deeper: the D2H copy of batch i is queued on its own stream behind an event, batch i+1 is launched, and only then
     is batch i handed out, so the device never waits for the host to read a result and relaunch.  ``post`` (optional)
     maps the device outputs of a batch to the dict that is handed out / copied, on the compute stream right after the
-    forward (the multi-GPU result gather, ``shard.gather_outputs``).
+    forward (the multi-GPU result gather, ``shard.gather_outputs``).  ``to_host="defer"`` runs the same one-deeper
+    pipeline but hands out the DEVICE outputs (no D2H): what the ranks other than the consumer of a gathered result do.
 
     A batch whose pair lists overflowed their capacity (one-call path; ``Net.check``) is recomputed with
     ``Net.forward`` before it is handed out."""
@@ -1433,7 +1434,9 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
         copied.synchronize()
         if net.check(b):
             out = redo(b)
-            return {k: [t.cpu() for t in out[k]] for k in ("cls", "reg")}
+            return out if to_host == "defer" else {k: [t.cpu() for t in out[k]] for k in ("cls", "reg")}
+        if to_host == "defer":
+            return {"cls": cls_h, "reg": reg_h}
         return {"cls": list(cls_h.split_with_sizes(sizes)), "reg": list(reg_h.split_with_sizes(sizes))}
 
     held = None   # (cls_host, reg_host, sizes, copied event, batch) of the previous batch
@@ -1441,7 +1444,11 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
         out = net.forward_device(staged)          # enqueued; no host synchronisation on the one-call path
         if post is not None:
             out = post(out)
-        if to_host:
+        if to_host == "defer":
+            done = torch.cuda.Event()
+            done.record()
+            mine = (out["cls"], out["reg"], None, done, staged)
+        elif to_host:
             dev = out["cls"][0].device if out["cls"] else net._device()
             with torch.cuda.device(dev):
                 cur, d2h = torch.cuda.current_stream(), _side_stream(dev, "d2h")

@@ -24,7 +24,24 @@ def source_available() -> bool:
 
 
 def built_available() -> bool:
-    return os.path.isfile(os.path.join(BUILT_DIR, "lanegcn.pyc"))
+    return os.path.isfile(os.path.join(BUILT_DIR, "lanegcn.refbc"))
+
+
+class _BuiltFinder:
+    """sys.meta_path finder for the byte-compiled reference modules in oracle/_ref (``<module>.refbc`` = CPython
+    bytecode; the reference's modules import each other by bare name, so they are resolved here)."""
+
+    NAMES = ("lanegcn", "layers", "utils", "data")
+
+    @classmethod
+    def find_spec(cls, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+
+        f = os.path.join(BUILT_DIR, name + ".refbc")
+        if name not in cls.NAMES or not os.path.isfile(f):
+            return None
+        return importlib.util.spec_from_file_location(name, f, loader=importlib.machinery.SourcelessFileLoader(name, f))
 
 
 def available() -> bool:
@@ -54,8 +71,11 @@ def load(keep_gpu: bool = False):
     sys.modules["argoverse.data_loading.argoverse_forecasting_loader"].ArgoverseForecastingLoader = object
     sys.modules["argoverse.map_representation.map_api"].ArgoverseMap = object
     sys.modules["skimage.transform"].rotate = None
-    if ref_dir not in sys.path:
-        sys.path.insert(0, ref_dir)
+    if source_available():
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+    elif _BuiltFinder not in sys.meta_path:
+        sys.meta_path.insert(0, _BuiltFinder)
     # the reference imports its siblings by bare name ("data", "utils", "layers"): make sure nothing of
     # ours shadows them, then restore sys.path so those generic names do not leak into later imports.
     import lanegcn as ref_lanegcn  # noqa: E402
