@@ -292,6 +292,36 @@ typedef struct LgcnForwardArgs {
   void* workspace;                            /* lgcn_forward_workspace_bytes(&args)                               */
 } LgcnForwardArgs;
 
+/* ------------------------------------------------------------------ ActorNet (lanegcn.py:212-263) as ONE kernel
+ * feats [n_actors, 20, 3] (the concatenated per-actor histories as the dataset stores them: step-major, i.e. BEFORE the
+ * transpose of actor_gather) -> out [n_actors, 128] = output Res1d at the last step.  fp32 FMA arithmetic.
+ * wpack (lgcn_actor_net_wpack_floats floats) is written by lgcn_actor_net_pack from the 20 conv layers in this order:
+ *   groups.g.0.{conv1,conv2,downsample.0}, groups.g.1.{conv1,conv2}  for g = 0,1,2;  lateral.0, lateral.1, lateral.2;
+ *   output.{conv1,conv2}
+ * with h_conv_w[i] the Conv1d weight [C_out, C_in, k] and h_gamma[i] / h_beta[i] the GroupNorm that follows it
+ * (HOST arrays of 20 DEVICE pointers).  n_actors_dev (may be NULL): live actor count in device memory.               */
+int64_t lgcn_actor_net_wpack_floats(void);
+int lgcn_actor_net_pack(const float* const* h_conv_w, const float* const* h_gamma, const float* const* h_beta,
+                        float* wpack, void* stream);
+int lgcn_actor_net(const float* feats, const float* wpack, float* out, int64_t n_actors, const int32_t* n_actors_dev,
+                   void* stream);
+
+/* ------------------------------------------------------------------ PredNet + AttDest + sort + world transform, ONE kernel
+ * (lanegcn.py:575-631, 713-737, 145-150).  actors [n,128], actor_ctrs [n,2] -> cls [n,6] (descending), reg [n,6,30,2]
+ * (trajectories in the order of their scores; in world coordinates reg . rot[b] + orig[b] of the actor's scene b when
+ * rot != NULL, else in scene coordinates as PredNet.forward returns them).  actor_off int32[n_scenes + 1].
+ * wpack (lgcn_pred_net_wpack_floats floats) is written by lgcn_pred_net_pack from 64 DEVICE pointers (HOST array):
+ *   for m in 0..5: pred.m.0.linear1.weight, pred.m.0.linear2.weight, pred.m.0.norm1.{weight,bias},
+ *                  pred.m.0.norm2.{weight,bias}, pred.m.1.weight [60,128], pred.m.1.bias
+ *   att_dest.dist.0.{weight [128,2],bias}, att_dest.dist.2.linear.weight, att_dest.dist.2.norm.{weight,bias},
+ *   att_dest.agt.linear.weight [128,256], att_dest.agt.norm.{weight,bias}
+ *   cls.0.linear1.weight, cls.0.linear2.weight, cls.0.norm1.{weight,bias}, cls.0.norm2.{weight,bias}, cls.1.weight, cls.1.bias */
+int64_t lgcn_pred_net_wpack_floats(void);
+int lgcn_pred_net_pack(const float* const* h_params, float* wpack, void* stream);
+int lgcn_pred_net(const float* actors, const float* actor_ctrs, const int32_t* actor_off, int n_scenes, const float* rot,
+                  const float* orig, const float* wpack, float* cls, float* reg, int64_t n_actors,
+                  const int32_t* n_actors_dev, void* stream);
+
 /* World transform of the predictions (lanegcn.py:145-150): reg[a, :, :, :] <- reg[a] . rot[b] + orig[b] with b the
  * scene of actor a (actor_off int32[n_scenes + 1], padded with the total), in place; reg holds points_per_actor
  * (= num_mods x num_preds) float2 per actor.  n_actors_dev (may be NULL): live actor count in device memory.      */

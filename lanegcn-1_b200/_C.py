@@ -59,6 +59,12 @@ _SIGS = {
     "lgcn_att_wpack_floats": (_i64, []),
     "lgcn_att_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_actor_gather": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "lgcn_actor_net_wpack_floats": (_i64, []),
+    "lgcn_actor_net_pack": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "lgcn_actor_net": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "lgcn_pred_net_wpack_floats": (_i64, []),
+    "lgcn_pred_net_pack": (_i32, [_vp, _vp, _vp]),
+    "lgcn_pred_net": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "lgcn_world_transform": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
     "lgcn_forward_prepared_bytes": (_i64, [_i32]),
     "lgcn_forward_prepare": (_i32, [_vp, _i32, _vp]),

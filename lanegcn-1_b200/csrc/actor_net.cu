@@ -1,0 +1,350 @@
+// actor_net.cu — ActorNet (lanegcn.py:212-263; layers.py:40-62 Conv1d, :142-190 Res1d) as ONE kernel.
+//
+// The reference runs ~20 Conv1d + GroupNorm(1) + ReLU layers over [A, C, L] (A actors, L = 20/10/5 steps,
+// C = 3/32/64/128): on a GPU that is ~110 tiny cuDNN / ATen launches whose activations bounce through HBM.  Here a CTA
+// takes kActors actors through the WHOLE network with every activation resident in shared memory (channels-last:
+// [actor][step + 2 zero pad rows][channel]); only the 3x20 input and the 128-float result touch HBM.  Weights stream
+// from L2 through a shared-memory stage (re-packed once per weight version as [tap][c_in][c_out], so a warp reads 512
+// contiguous bytes).  Arithmetic is plain fp32 FMA (the reference's convs are true fp32: cudnn.allow_tf32 = False):
+// 8.6 MFLOP per actor, compute-bound on the FP32 pipe; GroupNorm(1) normalises over all (C, L) of an actor, two-pass.
+//
+// Thread mapping of a conv (a [rows = actors x L_out] x [K = taps x C_in] x [C_out] product): a lane owns 4 output
+// channels (distinct, coalesced weight reads) x RT consecutive steps of one actor (input rows are warp-broadcast
+// 128-bit shared loads): 4 x RT x 4 FMAs per 4 + RT shared loads.
+#include <atomic>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kActors = 4;      // actors per CTA
+constexpr int kThreads = 256;
+constexpr int kWChunk = 16;     // input channels per staged weight chunk (x 3 taps x 128 outputs x 4 B = 24 KB)
+
+struct ConvW {
+  const float* w;       // [K][CinP][Cout]
+  const float* gamma;   // [Cout]
+  const float* beta;    // [Cout]
+};
+
+// float offsets of the 20 layers inside the pack (lgcn_actor_net_wpack_floats documents the order)
+struct Spec { int cin, cout, k; };
+__host__ __device__ constexpr int cin_padded(int c) { return c < 4 ? 4 : c; }
+__host__ __device__ constexpr Spec spec(int i) {
+  constexpr Spec t[20] = {
+      {3, 32, 3}, {32, 32, 3}, {3, 32, 1}, {32, 32, 3}, {32, 32, 3},            // groups.0
+      {32, 64, 3}, {64, 64, 3}, {32, 64, 1}, {64, 64, 3}, {64, 64, 3},          // groups.1
+      {64, 128, 3}, {128, 128, 3}, {64, 128, 1}, {128, 128, 3}, {128, 128, 3},  // groups.2
+      {32, 128, 3}, {64, 128, 3}, {128, 128, 3},                                // lateral.0/1/2
+      {128, 128, 3}, {128, 128, 3}};                                            // output
+  return t[i];
+}
+__host__ __device__ constexpr int64_t spec_floats(int i) {
+  return (int64_t)spec(i).k * cin_padded(spec(i).cin) * spec(i).cout + 2 * spec(i).cout;
+}
+__host__ __device__ constexpr int64_t spec_offset(int i) {
+  int64_t o = 0;
+  for (int j = 0; j < i; ++j) o += spec_floats(j);
+  return o;
+}
+template <int I>
+__device__ __forceinline__ ConvW layer(const float* pack) {
+  constexpr int64_t off = spec_offset(I), nw = (int64_t)spec(I).k * cin_padded(spec(I).cin) * spec(I).cout;
+  constexpr int cout = spec(I).cout;
+  ConvW c;
+  c.w = pack + off;
+  c.gamma = c.w + nw;
+  c.beta = c.gamma + cout;
+  return c;
+}
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// Raw convolution: in [G][LIN + 2][CIN] -> out rows 1..LOUT of [G][LOUT + 2][COUT]   (LIN = LOUT * STRIDE; K = 3: pad 1,
+// K = 1: pad 0).  All threads of the CTA call it; ends with a __syncthreads().
+template <int CIN, int COUT, int K, int STRIDE, int LOUT, int RT>
+__device__ __forceinline__ void conv(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ Wt,
+                                     float* __restrict__ wst) {
+  constexpr int LIN = LOUT * STRIDE;
+  constexpr int LPG = COUT / 4;              // lanes per row group
+  constexpr int GROUPS = kThreads / LPG;     // row groups in the CTA
+  constexpr int TILES_PER_ACTOR = LOUT / RT;
+  constexpr int N_TILES = kActors * TILES_PER_ACTOR;
+  constexpr int NR = K == 3 ? (RT - 1) * STRIDE + 3 : RT;   // input rows a tile touches
+  constexpr int CH = CIN < kWChunk ? CIN : kWChunk;
+  static_assert(LOUT % RT == 0 && COUT % 4 == 0 && CIN % 4 == 0 && CIN % CH == 0, "shape");
+  const int co0 = (threadIdx.x % LPG) * 4;
+  const int group = threadIdx.x / LPG;
+
+  for (int tile0 = 0; tile0 < N_TILES; tile0 += GROUPS) {
+    const int tile = tile0 + group;
+    const bool live = tile < N_TILES;
+    const int g = live ? tile / TILES_PER_ACTOR : 0, l0 = live ? (tile % TILES_PER_ACTOR) * RT : 0;
+    // first input row (padded coordinates) of the tile: K = 3 -> l0 * S + kk, K = 1 -> l0 * S + 1
+    const float* xin = in + ((int64_t)g * (LIN + 2) + l0 * STRIDE + (K == 3 ? 0 : 1)) * CIN;
+    float acc[RT][4];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    for (int c0 = 0; c0 < CIN; c0 += CH) {
+      __syncthreads();   // the previous chunk (or the producer of `in`) is done with wst / has written `in`
+      for (int i = threadIdx.x; i < K * CH * COUT / 4; i += kThreads) {   // wst[kk][ci][co] <- Wt[kk][c0 + ci][co]
+        const int co4 = i % (COUT / 4), ci = (i / (COUT / 4)) % CH, kk = i / (COUT / 4 * CH);
+        reinterpret_cast<float4*>(wst)[i] =
+            __ldg(reinterpret_cast<const float4*>(Wt + ((int64_t)kk * CIN + c0 + ci) * COUT) + co4);
+      }
+      __syncthreads();
+      if (live) {
+#pragma unroll 1
+        for (int ci = 0; ci < CH; ci += 4) {
+          float4 x[NR];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) x[r] = lds4(xin + (K == 3 ? r : r * STRIDE) * CIN + c0 + ci);
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk) {
+            const float* wp = wst + ((int64_t)kk * CH + ci) * COUT + co0;
+            const float4 w0 = lds4(wp), w1 = lds4(wp + COUT), w2 = lds4(wp + 2 * COUT), w3 = lds4(wp + 3 * COUT);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              const float4 v = x[K == 3 ? r * STRIDE + kk : r];
+              acc[r][0] = fmaf(v.w, w3.x, fmaf(v.z, w2.x, fmaf(v.y, w1.x, fmaf(v.x, w0.x, acc[r][0]))));
+              acc[r][1] = fmaf(v.w, w3.y, fmaf(v.z, w2.y, fmaf(v.y, w1.y, fmaf(v.x, w0.y, acc[r][1]))));
+              acc[r][2] = fmaf(v.w, w3.z, fmaf(v.z, w2.z, fmaf(v.y, w1.z, fmaf(v.x, w0.z, acc[r][2]))));
+              acc[r][3] = fmaf(v.w, w3.w, fmaf(v.z, w2.w, fmaf(v.y, w1.w, fmaf(v.x, w0.w, acc[r][3]))));
+            }
+          }
+        }
+      }
+    }
+    if (live) {
+      float* o = out + ((int64_t)g * (LOUT + 2) + l0 + 1) * COUT + co0;
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+        *reinterpret_cast<float4*>(o + (int64_t)r * COUT) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+  }
+  __syncthreads();
+}
+
+enum { GN_RELU = 1, GN_ADD_RES = 2, GN_ACCUM = 4 };
+// GroupNorm(1 group over all C x L of an actor; layers.py:52 / :158, eps 1e-5, biased variance) of the raw rows
+// 1..L of `src`, then  v = norm * gamma + beta  [+ res]  [relu]  ->  dst (= v, or += v with GN_ACCUM).  dst may be src.
+// Also zeroes dst's two pad rows.  Ends with a __syncthreads().
+template <int C, int L>
+__device__ __forceinline__ void gn_apply(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, const float* __restrict__ res, int flags,
+                                         float* __restrict__ stats) {
+  constexpr int N = C * L, STR = (L + 2) * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < kActors) {
+    const float* p = src + (int64_t)warp * STR + C;
+    float s = 0.f;
+    for (int i = lane * 4; i < N; i += 128) {
+      const float4 v = lds4(p + i);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(s) * (1.0f / N);
+    float q = 0.f;
+    for (int i = lane * 4; i < N; i += 128) {
+      const float4 v = lds4(p + i);
+      const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = warp_sum(q) * (1.0f / N);
+    if (lane == 0) {
+      stats[2 * warp] = mean;
+      stats[2 * warp + 1] = 1.0f / sqrtf(var + LGCN_GN_EPS);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kActors * N / 4; i += kThreads) {
+    const int g = i / (N / 4), e = (i % (N / 4)) * 4, c = e % C;
+    const float mean = stats[2 * g], rstd = stats[2 * g + 1];
+    const int64_t at = (int64_t)g * STR + C + e;
+    const float4 v = lds4(src + at), ga = __ldg(reinterpret_cast<const float4*>(gamma + c)),
+                 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y = make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
+                           (v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w);
+    if (flags & GN_ADD_RES) {
+      const float4 r = lds4(res + at);
+      y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+    }
+    if (flags & GN_RELU) y = relu4(y);
+    if (flags & GN_ACCUM) {
+      const float4 d = lds4(dst + at);
+      y.x += d.x; y.y += d.y; y.z += d.z; y.w += d.w;
+    }
+    *reinterpret_cast<float4*>(dst + at) = y;
+  }
+  for (int i = threadIdx.x; i < kActors * 2 * C; i += kThreads) {   // pad rows 0 and L + 1
+    const int g = i / (2 * C), r = (i / C) & 1, c = i % C;
+    dst[(int64_t)g * STR + (r ? (L + 1) * C : 0) + c] = 0.f;
+  }
+  __syncthreads();
+}
+
+// y = relu(a + b) on rows 1..L (the tail of a Res1d with a down-sampled shortcut), in place into a
+template <int C, int L>
+__device__ __forceinline__ void add_relu(float* __restrict__ a, const float* __restrict__ b) {
+  constexpr int N = C * L, STR = (L + 2) * C;
+  for (int i = threadIdx.x; i < kActors * N / 4; i += kThreads) {
+    const int64_t at = (int64_t)(i / (N / 4)) * STR + C + (i % (N / 4)) * 4;
+    const float4 x = lds4(a + at), y = lds4(b + at);
+    *reinterpret_cast<float4*>(a + at) = relu4(make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+  }
+  __syncthreads();
+}
+
+// F.interpolate(scale_factor=2, mode="linear", align_corners=False) along the steps (lanegcn.py:259):
+// out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1], edges clamped.  src [G][L+2][C] -> dst [G][2L+2][C]
+template <int C, int L>
+__device__ __forceinline__ void upsample2(const float* __restrict__ src, float* __restrict__ dst) {
+  constexpr int SS = (L + 2) * C, DS = (2 * L + 2) * C;
+  for (int i = threadIdx.x; i < kActors * 2 * L * C / 4; i += kThreads) {
+    const int c = (i % (C / 4)) * 4, j = (i / (C / 4)) % (2 * L), g = i / (C / 4 * 2 * L);
+    const int k = j >> 1;
+    const int nb = (j & 1) ? (k + 1 < L ? k + 1 : L - 1) : (k > 0 ? k - 1 : 0);
+    const float4 x = lds4(src + (int64_t)g * SS + (k + 1) * C + c), y = lds4(src + (int64_t)g * SS + (nb + 1) * C + c);
+    // torch: w0 * x[i0] + w1 * x[i1] with (w0, w1) = (0.75, 0.25) on the near / far sample
+    *reinterpret_cast<float4*>(dst + (int64_t)g * DS + (j + 1) * C + c) =
+        make_float4(0.75f * x.x + 0.25f * y.x, 0.75f * x.y + 0.25f * y.y, 0.75f * x.z + 0.25f * y.z, 0.75f * x.w + 0.25f * y.w);
+  }
+  for (int i = threadIdx.x; i < kActors * 2 * C; i += kThreads) {
+    const int g = i / (2 * C), r = (i / C) & 1, c = i % C;
+    dst[(int64_t)g * DS + (r ? (2 * L + 1) * C : 0) + c] = 0.f;
+  }
+  __syncthreads();
+}
+
+// shared memory (floats)
+constexpr int kBig = kActors * 22 * 128;                          // a [G][20 + 2][128] buffer
+constexpr int kOffX0 = 0;                                         // input [G][22][4]
+constexpr int kOffP = kOffX0 + kActors * 22 * 4;
+constexpr int kOffQ = kOffP + kBig;
+constexpr int kOffR = kOffQ + kBig;
+constexpr int kOffF0 = kOffR + kBig;                              // [G][22][32]
+constexpr int kOffF1 = kOffF0 + kActors * 22 * 32;                // [G][12][64]
+constexpr int kOffF2 = kOffF1 + kActors * 12 * 64;                // [G][7][128]
+constexpr int kOffW = kOffF2 + kActors * 7 * 128;                 // weight stage [3][kWChunk][128]
+constexpr int kOffStat = kOffW + 3 * kWChunk * 128;
+constexpr int kSmemFloats = kOffStat + 2 * kActors + 8;
+constexpr int kSmemBytes = kSmemFloats * 4;
+
+// Res1d (layers.py:142-190): x -> relu(GN(conv2(relu(GN(conv1(x))))) + shortcut); h, y: scratch; result in `dst`
+template <int CIN, int COUT, int STRIDE, int LOUT, int RT, int I1, int I2, int ID>
+__device__ __forceinline__ void res1d(const float* x, float* h, float* y, float* d, float* dst, const float* pack, float* wst,
+                                      float* stats) {
+  const ConvW c1 = layer<I1>(pack), c2 = layer<I2>(pack);
+  conv<CIN, COUT, 3, STRIDE, LOUT, RT>(x, h, c1.w, wst);
+  gn_apply<COUT, LOUT>(h, h, c1.gamma, c1.beta, nullptr, GN_RELU, stats);
+  conv<COUT, COUT, 3, 1, LOUT, RT>(h, y, c2.w, wst);
+  if constexpr (ID >= 0) {
+    const ConvW cd = layer<ID>(pack);
+    gn_apply<COUT, LOUT>(y, y, c2.gamma, c2.beta, nullptr, 0, stats);
+    conv<CIN, COUT, 1, STRIDE, LOUT, RT>(x, d, cd.w, wst);
+    gn_apply<COUT, LOUT>(d, d, cd.gamma, cd.beta, nullptr, 0, stats);
+    add_relu<COUT, LOUT>(y, d);   // the blocks with a shortcut conv leave their result in y (dst == y)
+  } else {
+    gn_apply<COUT, LOUT>(y, dst, c2.gamma, c2.beta, x, GN_ADD_RES | GN_RELU, stats);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __restrict__ pack, float* __restrict__ out /* [A][128] */,
+            int64_t a_cap, const int32_t* __restrict__ a_dev) {
+  extern __shared__ __align__(16) float sm[];
+  const int64_t A = lgcn_devn(a_dev, a_cap);
+  const int64_t a0 = (int64_t)blockIdx.x * kActors;
+  if (a0 >= A) return;
+  float *X0 = sm + kOffX0, *P = sm + kOffP, *Q = sm + kOffQ, *R = sm + kOffR, *F0 = sm + kOffF0, *F1 = sm + kOffF1,
+        *F2 = sm + kOffF2, *wst = sm + kOffW, *stats = sm + kOffStat;
+  // input: [A][20][3] (dx, dy, valid per step; lanegcn.py:155-168 transposes it to channels-first for Conv1d — the
+  // channels-last layout used here is the untransposed one) -> [G][22][4], zero pads and zero 4th channel
+  for (int i = threadIdx.x; i < kActors * 22; i += kThreads) {
+    const int g = i / 22, r = i % 22;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 1 && r <= 20 && a0 + g < A) {
+      const float* p = feats + ((a0 + g) * 20 + (r - 1)) * 3;
+      v = make_float4(p[0], p[1], p[2], 0.f);
+    }
+    reinterpret_cast<float4*>(X0)[i] = v;
+  }
+  __syncthreads();
+  // groups.0 (L = 20, 32 channels)
+  res1d<4, 32, 1, 20, 10, 0, 1, 2>(X0, P, Q, R, Q, pack, wst, stats);      // -> Q
+  res1d<32, 32, 1, 20, 10, 3, 4, -1>(Q, P, R, nullptr, F0, pack, wst, stats);   // -> F0
+  // groups.1 (L = 10, 64 channels)
+  res1d<32, 64, 2, 10, 5, 5, 6, 7>(F0, P, Q, R, Q, pack, wst, stats);
+  res1d<64, 64, 1, 10, 5, 8, 9, -1>(Q, P, R, nullptr, F1, pack, wst, stats);
+  // groups.2 (L = 5, 128 channels)
+  res1d<64, 128, 2, 5, 5, 10, 11, 12>(F1, P, Q, R, Q, pack, wst, stats);
+  res1d<128, 128, 1, 5, 5, 13, 14, -1>(Q, P, R, nullptr, F2, pack, wst, stats);
+  // FPN: out = lateral2(f2); out = up(out) + lateral1(f1); out = up(out) + lateral0(f0)            lanegcn.py:256-261
+  {
+    const ConvW l2 = layer<17>(pack), l1 = layer<16>(pack), l0 = layer<15>(pack);
+    conv<128, 128, 3, 1, 5, 5>(F2, P, l2.w, wst);
+    gn_apply<128, 5>(P, P, l2.gamma, l2.beta, nullptr, 0, stats);
+    upsample2<128, 5>(P, Q);
+    conv<64, 128, 3, 1, 10, 5>(F1, R, l1.w, wst);
+    gn_apply<128, 10>(R, Q, l1.gamma, l1.beta, nullptr, GN_ACCUM, stats);
+    upsample2<128, 10>(Q, P);
+    conv<32, 128, 3, 1, 20, 10>(F0, R, l0.w, wst);
+    gn_apply<128, 20>(R, P, l0.gamma, l0.beta, nullptr, GN_ACCUM, stats);
+  }
+  // output Res1d, last step only                                                                  lanegcn.py:262
+  res1d<128, 128, 1, 20, 10, 18, 19, -1>(P, Q, R, nullptr, R, pack, wst, stats);
+  for (int i = threadIdx.x; i < kActors * 32; i += kThreads) {
+    const int g = i >> 5, c = (i & 31) * 4;
+    if (a0 + g < A)
+      *reinterpret_cast<float4*>(out + (a0 + g) * LGCN_C + c) = lds4(R + (int64_t)g * 22 * 128 + 20 * 128 + c);
+  }
+}
+
+// conv.weight [Cout][Cin][K] (torch) -> [K][CinP][Cout]; one thread per output element
+__global__ void k_pack_conv(const float* __restrict__ w, float* __restrict__ dst, int cin, int cinp, int cout, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * cinp * cout) return;
+  const int co = i % cout, ci = (i / cout) % cinp, kk = i / (cout * cinp);
+  dst[i] = ci < cin ? w[((int64_t)co * cin + ci) * k + kk] : 0.f;
+}
+
+std::atomic<int> g_attr[64];
+
+}  // namespace
+
+extern "C" int64_t lgcn_actor_net_wpack_floats(void) { return spec_offset(20); }
+
+extern "C" int lgcn_actor_net_pack(const float* const* h_conv_w, const float* const* h_gamma, const float* const* h_beta,
+                                   float* wpack, void* stream) {
+  LGCN_CHECK_ARG(h_conv_w && h_gamma && h_beta && wpack, "actor_net_pack: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < 20; ++i) {
+    const Spec s = spec(i);
+    const int cp = cin_padded(s.cin), n = s.k * cp * s.cout;
+    LGCN_CHECK_ARG(h_conv_w[i] && h_gamma[i] && h_beta[i], "actor_net_pack: NULL layer %d", i);
+    float* dst = wpack + spec_offset(i);
+    k_pack_conv<<<lgcn_cdiv(n, 256), 256, 0, st>>>(h_conv_w[i], dst, s.cin, cp, s.cout, s.k);
+    LGCN_LAUNCH_OK();
+    LGCN_CUDA_OK(cudaMemcpyAsync(dst + n, h_gamma[i], s.cout * 4, cudaMemcpyDeviceToDevice, st));
+    LGCN_CUDA_OK(cudaMemcpyAsync(dst + n + s.cout, h_beta[i], s.cout * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int lgcn_launch_actor_net(const float* feats, const float* wpack, float* out, int64_t a_cap, const int32_t* a_dev,
+                          cudaStream_t st) {
+  if (a_cap <= 0) return 0;
+  int dev = 0;
+  LGCN_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && g_attr[dev].exchange(1) == 0)
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_actor_net, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  k_actor_net<<<lgcn_cdiv(a_cap, kActors), kThreads, kSmemBytes, st>>>(feats, wpack, out, a_cap, a_dev);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lgcn_actor_net(const float* feats, const float* wpack, float* out, int64_t n_actors,
+                              const int32_t* n_actors_dev, void* stream) {
+  LGCN_CHECK_ARG(n_actors >= 0, "actor_net: n_actors %lld", (long long)n_actors);
+  LGCN_CHECK_ARG(n_actors == 0 || (feats && wpack && out), "actor_net: NULL argument");
+  return lgcn_launch_actor_net(feats, wpack, out, n_actors, n_actors_dev, (cudaStream_t)stream);
+}

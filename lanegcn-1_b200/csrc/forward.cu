@@ -103,8 +103,8 @@ __global__ void k_world_transform(float2* __restrict__ reg, const int32_t* __res
   const int64_t total = lgcn_devn(n_dev, a_cap) * pts;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = scene_of(actor_off, n_scenes, (int32_t)(i / pts));
-    const float4 r = reinterpret_cast<const float4*>(rot)[b];   // r00 r01 r10 r11
-    const float2 o = reinterpret_cast<const float2*>(orig)[b];
+    const float4 r = make_float4(rot[4 * b], rot[4 * b + 1], rot[4 * b + 2], rot[4 * b + 3]);   // r00 r01 r10 r11
+    const float2 o = make_float2(orig[2 * b], orig[2 * b + 1]);
     const float2 x = reg[i];
     reg[i] = make_float2(__fadd_rn(__fadd_rn(__fmul_rn(x.x, r.x), __fmul_rn(x.y, r.z)), o.x),
                          __fadd_rn(__fadd_rn(__fmul_rn(x.x, r.y), __fmul_rn(x.y, r.w)), o.y));

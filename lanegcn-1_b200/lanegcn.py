@@ -1018,6 +1018,8 @@ class Net(nn.Module):
         for fw in self._fw.values():
             for wp in fw.packs.values():
                 wp.invalidate()
+        self.actor_net._pp.invalidate()
+        self.pred_net._pp.invalidate()
 
     # ------------------------------------------------------------------ weights of the one-call path
     def _weights(self, dev) -> _ForwardWeights:
@@ -1034,7 +1036,10 @@ class Net(nn.Module):
         m2m = self.m2m._wpack()
         wps = [fw.packs["map_input"], fw.packs["map_seg"], mn._wp, fw.packs["a2m_meta"], self.m2m._wp] + \
               [att._wp for att in list(self.a2m.att) + list(self.m2a.att) + list(self.a2a.att)]
+        self.actor_net.wpack()   # refreshed here (outside any capture); their kernels read the packs in place
+        self.pred_net.wpack()
         key = tuple((w.buf.data_ptr(), w.version) for w in wps)
+        fw.ptrs = tuple(w.buf.data_ptr() for w in wps) + (self.actor_net._pp.buf.data_ptr(), self.pred_net._pp.buf.data_ptr())
         if key != fw.key:
             st = fw.struct
             st.map_input, st.map_seg, st.map_fuse, st.a2m_meta = (t.data_ptr() for t in packs)
@@ -1251,10 +1256,15 @@ class Net(nn.Module):
         a.w = fw.struct
         cur, side = torch.cuda.current_stream(), _side_stream(dev)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):   # ActorNet is independent of the map: a parallel branch
-            _C.check(lib.lgcn_actor_gather(slot.actor_feats.data_ptr(), slot.actors_t.data_ptr(), slot.caps.actors, 20, 3,
-                                           side.cuda_stream), "actor_gather")
-            slot.actors.copy_(self.actor_net(slot.actors_t))                                  # lanegcn.py:129-131
+        torch_blocks = os.environ.get("LGCN_TORCH_BLOCKS", "0") == "1"
+        n_act_dev = slot.dims[1:]
+        with torch.cuda.stream(side):   # ActorNet is independent of the map: a parallel branch      lanegcn.py:129-131
+            if torch_blocks:
+                _C.check(lib.lgcn_actor_gather(slot.actor_feats.data_ptr(), slot.actors_t.data_ptr(), slot.caps.actors, 20, 3,
+                                               side.cuda_stream), "actor_gather")
+                slot.actors.copy_(self.actor_net(slot.actors_t))
+            else:   # ONE kernel, straight from the step-major histories (the transpose of actor_gather is folded in)
+                self.actor_net.forward_ntc(slot.actor_feats, out=slot.actors, n_dev=n_act_dev)
 
         def run(stages):
             a.stages = stages
@@ -1271,13 +1281,17 @@ class Net(nn.Module):
                                         ("m2a", _C.STAGE_M2A, slot.actors, n_actors), ("a2a", _C.STAGE_A2A, slot.actors, n_actors)):
                 run(stage)
                 taps[name] = buf[:n].clone()
-        cls, reg = self.pred_net.core(slot.actors, slot.actor_ctrs)                           # :144
-        slot.cls.copy_(cls)
-        slot.reg.copy_(reg)
-        _C.check(lib.lgcn_world_transform(slot.reg.data_ptr(), slot.actor_off.data_ptr(), slot.caps.scenes,
-                                          slot.rot.data_ptr(), slot.orig.data_ptr(), slot.caps.actors,
-                                          slot.dims[1:].data_ptr(), slot.reg.shape[1] * slot.reg.shape[2],
-                                          cur.cuda_stream), "world_transform")                # :145-150
+        if torch_blocks:
+            cls, reg = self.pred_net.core(slot.actors, slot.actor_ctrs)                       # :144
+            slot.cls.copy_(cls)
+            slot.reg.copy_(reg)
+            _C.check(lib.lgcn_world_transform(slot.reg.data_ptr(), slot.actor_off.data_ptr(), slot.caps.scenes,
+                                              slot.rot.data_ptr(), slot.orig.data_ptr(), slot.caps.actors,
+                                              n_act_dev.data_ptr(), slot.reg.shape[1] * slot.reg.shape[2],
+                                              cur.cuda_stream), "world_transform")            # :145-150
+        else:   # PredNet + AttDest + sort + world transform: ONE kernel                               :144-150
+            self.pred_net.core(slot.actors, slot.actor_ctrs, slot.actor_off, slot.rot, slot.orig, cls=slot.cls, reg=slot.reg,
+                               n_dev=n_act_dev)
 
     @torch.no_grad()
     def forward_device(self, b: DeviceBatch, taps: Optional[Dict] = None) -> Dict[str, List[Tensor]]:
@@ -1293,14 +1307,14 @@ class Net(nn.Module):
                 cur.wait_event(slot.d2h_done)     # the previous results of this slot have been read back
             fw = self._weights(dev)
             if taps is None and self.use_cuda_graphs:
-                if slot.graph is None or slot.weights_version != fw.key:
+                if slot.graph is None or slot.weights_version != fw.ptrs:   # packs refresh in place: addresses only
                     self._run_slot(slot, fw, b.n_nodes, b.n_actors)      # warm-up: lazy initialisation outside capture
                     torch.cuda.synchronize(dev)
                     n0 = lib.lgcn_launch_count()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         self._run_slot(slot, fw, b.n_nodes, b.n_actors)
-                    slot.graph, slot.weights_version = g, fw.key
+                    slot.graph, slot.weights_version = g, fw.ptrs
                     slot.graph_kernels = int(lib.lgcn_launch_count() - n0)
                 slot.graph.replay()
                 self.replayed_kernels = getattr(self, "replayed_kernels", 0) + slot.graph_kernels
@@ -1332,9 +1346,13 @@ class Net(nn.Module):
             # ~1 ms at the start of every forward waiting for them; tools/trace_step.py)
             cur, side = torch.cuda.current_stream(), _side_stream(b.actors.device)
             side.wait_stream(cur)
+            torch_blocks = os.environ.get("LGCN_TORCH_BLOCKS", "0") == "1"
             with torch.cuda.stream(side):
-                x = b.actors.transpose(1, 2).contiguous()
-                actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
+                if torch_blocks:
+                    x = b.actors.transpose(1, 2).contiguous()
+                    actors = (self._g_actor(x) if self.use_cuda_graphs else self.actor_net(x))    # :129-131
+                else:
+                    actors = self.actor_net.forward_ntc(b.actors)
             actor_ctrs = b.actor_ctrs
             sizes = actor_ctrs.sizes
             actor_idcs = scene_list(torch.arange(sum(sizes), device=b.actors.device), sizes, actor_ctrs.off_dev,
@@ -1371,7 +1389,9 @@ class Net(nn.Module):
             if taps is not None:
                 taps["a2a"] = actors.clone()
             # PredNet + world transform (:144-150), batched over actors
-            if self.use_cuda_graphs:
+            if not torch_blocks:
+                cls, reg = self.pred_net.core(actors, actor_ctrs.cat, actor_ctrs.off_dev, b.rot, b.orig)
+            elif self.use_cuda_graphs:
                 cls, reg = self._g_pred(actors, actor_ctrs.cat, b.rot_a, b.orig_a)
                 cls, reg = cls.clone(), reg.clone()  # graph outputs are static buffers reused by the next replay
             else:

@@ -190,3 +190,43 @@ def test_second_device_if_present(lib):
                                         None, 0, y.data_ptr(), 128, 300, torch.cuda.current_stream().cuda_stream))
             assert_close(y, x.double().cpu() @ w.double().cpu().T, "linear on cuda:%d" % d)
     assert_close(outs[1], outs[0], "cuda:1 vs cuda:0", rtol=1e-5, atol=1e-5)
+
+
+# --------------------------------------------------------------------------- ActorNet / PredNet kernels (f2, f3)
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 64, 257])
+def test_actor_net_kernel_vs_oracle_and_torch(cuda, lib, net, n):
+    g = torch.Generator().manual_seed(n)
+    feats = torch.randn(n, 20, 3, generator=g) * 0.5
+    feats[:, :, 2] = (torch.rand(n, 20, generator=g) > 0.2).float()
+    feats[: n // 2, :7] = 0.0                                 # padded history prefix, as in the dataset
+    with torch.no_grad():
+        want = O.actor_net(weights(), feats.transpose(1, 2).contiguous())
+    got = net.actor_net(feats.transpose(1, 2).contiguous().to(cuda))       # module API: channels-first [A,3,20]
+    assert_close(got, want, f"actor_net kernel n={n}", rtol=1e-4, atol=2e-5)
+    got2 = net.actor_net.forward_ntc(feats.to(cuda))
+    assert torch.equal(got, got2)
+    ref = net.actor_net.forward_torch(feats.transpose(1, 2).contiguous().to(cuda))   # cuDNN fp32 spelling
+    assert_close(got, ref, "actor_net kernel vs torch", rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 100])
+def test_pred_net_kernel_vs_oracle(cuda, lib, net, n):
+    g = torch.Generator().manual_seed(10 + n)
+    actors = torch.randn(n, 128, generator=g)
+    ctrs = torch.randn(n, 2, generator=g) * 30
+    sizes = [n // 2, n - n // 2] if n > 1 else [1]
+    idcs = list(torch.arange(n).split(sizes))
+    with torch.no_grad():
+        want = O.pred_net(weights(), actors, idcs, list(ctrs.split(sizes)))
+    got = net.pred_net(actors.to(cuda), [i.to(cuda) for i in idcs], [c.to(cuda) for c in ctrs.split(sizes)])
+    assert [len(x) for x in got["cls"]] == sizes
+    assert_close(torch.cat(got["cls"]), torch.cat(want["cls"]), "cls")
+    assert_close(torch.cat(got["reg"]), torch.cat(want["reg"]), "reg")
+    # world transform folded in (lanegcn.py:145-150)
+    rot = torch.randn(len(sizes), 2, 2, generator=g)
+    orig = torch.randn(len(sizes), 2, generator=g) * 100
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    cls, reg = net.pred_net.core(actors.to(cuda), ctrs.to(cuda), off.to(cuda), rot.to(cuda), orig.to(cuda))
+    want_w = torch.cat([torch.matmul(r, rot[i]) + orig[i].view(1, 1, 1, -1) for i, r in enumerate(want["reg"])])
+    assert_close(reg, want_w, "reg (world)")
+    assert torch.equal(cls, torch.cat(got["cls"]))

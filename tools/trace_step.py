@@ -45,3 +45,8 @@ for e in ev:
 print("top kernels by total time:")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
     print(f"  {1e-3 * v[1]:7.3f} ms  x{v[0]:3d}  {k}")
+
+if len(sys.argv) > 2:   # full timeline: start offset, duration, stream, name
+    with open(sys.argv[2], "w") as f:
+        for e in ev:
+            f.write(f"{1e-3 * (e.time_range.start - t0):9.3f} {e.time_range.end - e.time_range.start:8.1f}us s{getattr(e, 'device_resource_id', '?')} {e.name[:90]}\n")
