@@ -17,9 +17,9 @@
 
 namespace {
 
-constexpr int kActors = 4;      // actors per CTA
-constexpr int kThreads = 256;
-constexpr int kWChunk = 16;     // input channels per staged weight chunk (x 3 taps x 128 outputs x 4 B = 24 KB)
+constexpr int kActors = 2;      // actors per CTA; 112 KB of shared memory per CTA -> two CTAs per SM, so one CTA's
+constexpr int kThreads = 128;   // barriers / GroupNorm passes overlap the other's FMA phases
+constexpr int kWChunk = 8;      // input channels per staged weight chunk (x 3 taps x 128 outputs x 4 B = 12 KB), two stages
 
 struct ConvW {
   const float* w;       // [K][CinP][Cout]
@@ -85,14 +85,24 @@ __device__ __forceinline__ void conv(const float* __restrict__ in, float* __rest
     float acc[RT][4];
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-    for (int c0 = 0; c0 < CIN; c0 += CH) {
-      __syncthreads();   // the previous chunk (or the producer of `in`) is done with wst / has written `in`
-      for (int i = threadIdx.x; i < K * CH * COUT / 4; i += kThreads) {   // wst[kk][ci][co] <- Wt[kk][c0 + ci][co]
+    // weight chunks stream through a two-stage cp.async ring: chunk c+1 is in flight while chunk c is consumed
+    auto prefetch = [&](int c0, int stage) {   // wst[stage][kk][ci][co] <- Wt[kk][c0 + ci][co]
+      float* dst = wst + stage * (3 * kWChunk * 128);
+      for (int i = threadIdx.x; i < K * CH * COUT / 4; i += kThreads) {
         const int co4 = i % (COUT / 4), ci = (i / (COUT / 4)) % CH, kk = i / (COUT / 4 * CH);
-        reinterpret_cast<float4*>(wst)[i] =
-            __ldg(reinterpret_cast<const float4*>(Wt + ((int64_t)kk * CIN + c0 + ci) * COUT) + co4);
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + 4 * i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Wt + ((int64_t)kk * CIN + c0 + ci) * COUT + 4 * co4)
+                     : "memory");
       }
-      __syncthreads();
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0, 0);
+    int stage = 0;
+    for (int c0 = 0; c0 < CIN; c0 += CH, stage ^= 1) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();   // chunk c0 has landed for every thread; everybody is done with the other stage (and with `in`'s producer)
+      if (c0 + CH < CIN) prefetch(c0 + CH, stage ^ 1);
+      const float* wcur = wst + stage * (3 * kWChunk * 128);
       if (live) {
 #pragma unroll 1
         for (int ci = 0; ci < CH; ci += 4) {
@@ -101,7 +111,7 @@ __device__ __forceinline__ void conv(const float* __restrict__ in, float* __rest
           for (int r = 0; r < NR; ++r) x[r] = lds4(xin + (K == 3 ? r : r * STRIDE) * CIN + c0 + ci);
 #pragma unroll
           for (int kk = 0; kk < K; ++kk) {
-            const float* wp = wst + ((int64_t)kk * CH + ci) * COUT + co0;
+            const float* wp = wcur + ((int64_t)kk * CH + ci) * COUT + co0;
             const float4 w0 = lds4(wp), w1 = lds4(wp + COUT), w2 = lds4(wp + 2 * COUT), w3 = lds4(wp + 3 * COUT);
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
@@ -115,6 +125,7 @@ __device__ __forceinline__ void conv(const float* __restrict__ in, float* __rest
         }
       }
     }
+    __syncthreads();   // (multi-round tiles only) the last chunk's stage is free before the next round's first prefetch
     if (live) {
       float* o = out + ((int64_t)g * (LOUT + 2) + l0 + 1) * COUT + co0;
 #pragma unroll
@@ -224,8 +235,8 @@ constexpr int kOffR = kOffQ + kBig;
 constexpr int kOffF0 = kOffR + kBig;                              // [G][22][32]
 constexpr int kOffF1 = kOffF0 + kActors * 22 * 32;                // [G][12][64]
 constexpr int kOffF2 = kOffF1 + kActors * 12 * 64;                // [G][7][128]
-constexpr int kOffW = kOffF2 + kActors * 7 * 128;                 // weight stage [3][kWChunk][128]
-constexpr int kOffStat = kOffW + 3 * kWChunk * 128;
+constexpr int kOffW = kOffF2 + kActors * 7 * 128;                 // weight stages 2 x [3][kWChunk][128]
+constexpr int kOffStat = kOffW + 2 * 3 * kWChunk * 128;
 constexpr int kSmemFloats = kOffStat + 2 * kActors + 8;
 constexpr int kSmemBytes = kSmemFloats * 4;
 
@@ -248,7 +259,7 @@ __device__ __forceinline__ void res1d(const float* x, float* h, float* y, float*
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __restrict__ pack, float* __restrict__ out /* [A][128] */,
             int64_t a_cap, const int32_t* __restrict__ a_dev) {
   extern __shared__ __align__(16) float sm[];

@@ -140,6 +140,10 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
 // exclusive scan: out[0..n] (n+1 entries) from cnt[0..n); scratch >= 1025 int32
 int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n_cap, const int32_t* n_dev, int32_t* scratch,
                                cudaStream_t st);
+// zero `bytes` (a multiple of 4) bytes at p with a KERNEL: inside a captured graph a kernel node carries the capture
+// stream's priority, a memset node does not (measured: memset nodes of the high-priority branch queued behind every
+// CTA of the low-priority ActorNet kernel)
+int lgcn_zero_async(void* p, int64_t bytes, cudaStream_t st);
 // ---- launchers whose row counts may live in device memory (n_dev != NULL: n_cap is the capacity that sizes the grid)
 int lgcn_launch_pack_meta(const float* turn, const float* control, const float* intersect, float* meta, int64_t n_cap,
                           const int32_t* n_dev, cudaStream_t st);

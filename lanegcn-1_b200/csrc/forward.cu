@@ -208,7 +208,7 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
   const int n_seg = 2 * L.n_keys * a.cap_scenes;
 
   if (a.stages & LGCN_STAGE_GRAPH) {
-    LGCN_CUDA_OK(cudaMemsetAsync(a.status, 0, 8 * sizeof(int32_t), st));
+    if (int rc = lgcn_zero_async(a.status, 8 * sizeof(int32_t), st)) return rc;
     // utils.to_long + the offset / cat loops of graph_gather (lanegcn.py:191-208)
     if (int rc = lgcn_offset_indices(a.local_idx, a.idx_bytes, a.segs, a.segs + n_seg + 1, n_seg, a.cap_index, e64, stream))
       return rc;

@@ -29,6 +29,18 @@ extern "C" int lgcn_offset_indices(const void* local, int idx_bytes, const int64
   return 0;
 }
 
+// ------------------------------------------------------------------ zero fill
+__global__ void k_zero(uint32_t* __restrict__ p, int64_t n_words) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+int lgcn_zero_async(void* p, int64_t bytes, cudaStream_t st) {
+  if (bytes <= 0) return 0;
+  LGCN_CHECK_ARG(bytes % 4 == 0 && ((uintptr_t)p & 3) == 0, "zero_async: unaligned");
+  k_zero<<<min(lgcn_cdiv(bytes / 4, 256), 148u * 4u), 256, 0, st>>>((uint32_t*)p, bytes / 4);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
 // ------------------------------------------------------------------ meta = cat(turn, control, intersect)
 __global__ void k_pack_meta(const float2* __restrict__ turn, const float* __restrict__ control,
                             const float* __restrict__ intersect, float4* __restrict__ meta, int64_t n_cap,
@@ -173,7 +185,7 @@ int lgcn_launch_exclusive_scan(const int32_t* cnt, int32_t* out, int64_t n_cap, 
   const int64_t nb = (n_cap + per - 1) / per;
   LGCN_CHECK_ARG(nb <= 1024, "exclusive_scan: %lld elements exceed the 4M-element limit", (long long)n_cap);
   if (nb == 0) {
-    LGCN_CUDA_OK(cudaMemsetAsync(out, 0, 4, st));
+    if (lgcn_zero_async(out, 4, st)) return -2;
     return 0;
   }
   k_scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, scratch, n_cap, n_dev);
@@ -292,8 +304,7 @@ static int csr_launch(const EdgeSets& es, const EdgeSets* es_dev, int64_t E_cap,
   int32_t* cnt = (int32_t*)workspace;
   int32_t* slot_edge = (int32_t*)((char*)workspace + lgcn_align_up(4 * n_cap, 256));
   int32_t* scan_scratch = (int32_t*)((char*)slot_edge + lgcn_align_up(4 * E_cap, 256));
-  LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_cap, st));
-  LGCN_CUDA_OK(cudaMemsetAsync(err_flag, 0, 4, st));
+  if (lgcn_zero_async(cnt, 4 * n_cap, st) || lgcn_zero_async(err_flag, 4, st)) return -2;
   const unsigned eb = E_cap ? min(lgcn_cdiv(E_cap, 256), 148u * 16u) : 0u;
   if (eb) {
     k_csr_hist<DEV><<<eb, 256, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, cnt, err_flag);
@@ -301,7 +312,7 @@ static int csr_launch(const EdgeSets& es, const EdgeSets* es_dev, int64_t E_cap,
   }
   if (lgcn_launch_exclusive_scan(cnt, rowptr, n_cap, n_dev, scan_scratch, st)) return -2;
   if (eb) {
-    LGCN_CUDA_OK(cudaMemsetAsync(cnt, 0, 4 * (size_t)n_cap, st));
+    if (lgcn_zero_async(cnt, 4 * n_cap, st)) return -2;
     k_csr_place<DEV><<<eb, 256, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, rowptr, cnt, slot_edge);
     LGCN_LAUNCH_OK();
     k_csr_finish<DEV><<<lgcn_cdiv(n_cap, 128), 128, 0, st>>>(es, es_dev, n_cap, n_dev, plain, rowptr, slot_edge, col);

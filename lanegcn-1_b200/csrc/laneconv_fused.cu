@@ -827,7 +827,7 @@ int lgcn_launch_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys
   LGCN_CHECK_ARG(plan && (n_nodes == 0 || rowptr), "plan_build: NULL argument");
   LGCN_CHECK_ARG(n_nodes >= 0 && n_edges >= 0 && n_nodes < (1ll << 31) / 16, "plan_build: sizes");
   PlanView v = plan_view(plan, n_nodes, n_edges, n_keys);
-  LGCN_CUDA_OK(cudaMemsetAsync(v.hdr, 0, 256, st));
+  if (int rc = lgcn_zero_async(v.hdr, 256, st)) return rc;
   const int64_t rows = (n_nodes + kTileM - 1) / kTileM * kTileM;
   if (rows == 0 || n_keys == 0) return 0;
   k_plan_build<<<lgcn_cdiv(rows, 256), 256, 0, st>>>(rowptr, col, n_keys, n_nodes, n_dev, v.hdr, v.tab, v.mdesc, v.mcol,

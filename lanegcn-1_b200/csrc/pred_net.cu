@@ -17,10 +17,9 @@
 
 namespace {
 
-constexpr int kGA = 16;        // actors per CTA
 constexpr int kModes = 6;
-constexpr int kThreads = 32 * kModes;
-constexpr int kPred = 60;      // 2 * num_preds
+constexpr int kThreads = 2 * 32 * kModes;   // two warps per mode, each owning half of the CTA's actors
+constexpr int kPred = 60;                   // 2 * num_preds
 constexpr int C = LGCN_C;
 
 // pack layout (floats); every matrix transposed to [in][out]
@@ -33,19 +32,19 @@ constexpr int64_t kPackFloats = kOffCls + kClsFloats;
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// acc[r][0..3] += sum_k in[r][k] * Wt[k][co0..co0+3]   for the kGA rows of `in` (shared, row stride ld)
-template <int KIN>
+// acc[r][0..3] += sum_k in[r][k] * Wt[k][co0..co0+3]   for RT rows of `in` (shared, row stride ld)
+template <int RT, int KIN>
 __device__ __forceinline__ void rows_fma(const float* __restrict__ in, int ld, const float* __restrict__ Wt, int nout,
-                                         int co0, float (&acc)[kGA][4]) {
+                                         int co0, float (&acc)[RT][4]) {
   if (co0 >= nout) return;
-#pragma unroll 1
+#pragma unroll 2
   for (int k = 0; k < KIN; k += 4) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)k * nout + co0));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)(k + 1) * nout + co0));
     const float4 w2 = __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)(k + 2) * nout + co0));
     const float4 w3 = __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)(k + 3) * nout + co0));
 #pragma unroll
-    for (int r = 0; r < kGA; ++r) {
+    for (int r = 0; r < RT; ++r) {
       const float4 v = lds4(in + r * ld + k);
       acc[r][0] = fmaf(v.w, w3.x, fmaf(v.z, w2.x, fmaf(v.y, w1.x, fmaf(v.x, w0.x, acc[r][0]))));
       acc[r][1] = fmaf(v.w, w3.y, fmaf(v.z, w2.y, fmaf(v.y, w1.y, fmaf(v.x, w0.y, acc[r][1]))));
@@ -55,79 +54,88 @@ __device__ __forceinline__ void rows_fma(const float* __restrict__ in, int ld, c
   }
 }
 
-__device__ __forceinline__ void zero(float (&acc)[kGA][4]) {
+template <int RT>
+__device__ __forceinline__ void zero(float (&acc)[RT][4]) {
 #pragma unroll
-  for (int r = 0; r < kGA; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
 }
 
-// rows <- [relu]( GN(rows) * gamma + beta [+ res] ), written to `out` (shared [kGA][128]); a warp holds whole rows
-__device__ __forceinline__ void gn_rows(float (&acc)[kGA][4], const float* __restrict__ gamma, const float* __restrict__ beta,
+// acc <- [relu]( GN(acc) * gamma + beta [+ res] ) in registers, and written to `out` (shared [RT][128]) unless NULL;
+// a warp holds whole rows (32 lanes x 4 channels)
+template <int RT>
+__device__ __forceinline__ void gn_rows(float (&acc)[RT][4], const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const float* __restrict__ res, bool relu, float* __restrict__ out, int lane) {
   const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane), b = __ldg(reinterpret_cast<const float4*>(beta) + lane);
 #pragma unroll
-  for (int r = 0; r < kGA; ++r) {
+  for (int r = 0; r < RT; ++r) {
     float4 y = warp_gn128(make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]), g, b);
     if (res) {
       const float4 x = lds4(res + r * C + lane * 4);
       y.x += x.x; y.y += x.y; y.z += x.z; y.w += x.w;
     }
     if (relu) y = relu4(y);
-    *reinterpret_cast<float4*>(out + r * C + lane * 4) = y;
+    acc[r][0] = y.x; acc[r][1] = y.y; acc[r][2] = y.z; acc[r][3] = y.w;
+    if (out) *reinterpret_cast<float4*>(out + r * C + lane * 4) = y;
   }
   __syncwarp();
 }
 
-// shared memory (floats)
-constexpr int kOffA = 0;                                   // actors [kGA][128]
-constexpr int kOffH1 = kOffA + kGA * C;                    // [modes][kGA][128]
-constexpr int kOffH2 = kOffH1 + kModes * kGA * C;
-constexpr int kOffH3 = kOffH2 + kModes * kGA * C;
-constexpr int kOffReg = kOffH3 + kModes * kGA * C;         // [kGA][modes][64]
-constexpr int kOffScore = kOffReg + kGA * kModes * 64;     // [kGA][8]
-constexpr int kOffCtr = kOffScore + kGA * 8;               // [kGA][2]
-constexpr int kSmemFloats = kOffCtr + kGA * 2;
-constexpr int kSmemBytes = kSmemFloats * 4;
+template <int RT>
+struct Smem {   // floats
+  static constexpr int GA = 2 * RT;                           // actors per CTA
+  static constexpr int offA = 0;                              // actors [GA][128]
+  static constexpr int offH1 = offA + GA * C;                 // [modes][GA][128]
+  static constexpr int offH2 = offH1 + kModes * GA * C;
+  static constexpr int offReg = offH2 + kModes * GA * C;      // [GA][modes][64]
+  static constexpr int offScore = offReg + GA * kModes * 64;  // [GA][8]
+  static constexpr int offCtr = offScore + GA * 8;            // [GA][2]
+  static constexpr int floats = offCtr + GA * 2;
+};
 
+template <int RT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pred_net(const float* __restrict__ actors, const float* __restrict__ ctrs, const int32_t* __restrict__ actor_off, int n_scenes,
            const float* __restrict__ rot, const float* __restrict__ orig, const float* __restrict__ pack,
            float* __restrict__ cls_out /* [A][6] */, float* __restrict__ reg_out /* [A][6][30][2] */, int64_t a_cap,
            const int32_t* __restrict__ a_dev) {
+  using S = Smem<RT>;
+  constexpr int GA = S::GA;
   extern __shared__ __align__(16) float sm[];
   const int64_t A = lgcn_devn(a_dev, a_cap);
-  const int64_t a0 = (int64_t)blockIdx.x * kGA;
+  const int64_t a0 = (int64_t)blockIdx.x * GA;
   if (a0 >= A) return;
-  const int m = threadIdx.x >> 5, lane = threadIdx.x & 31, co0 = lane * 4;
-  float *sA = sm + kOffA, *H1 = sm + kOffH1 + m * kGA * C, *H2 = sm + kOffH2 + m * kGA * C, *H3 = sm + kOffH3 + m * kGA * C,
-        *sReg = sm + kOffReg, *sScore = sm + kOffScore, *sCtr = sm + kOffCtr;
-  for (int i = threadIdx.x; i < kGA * 32; i += kThreads) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, co0 = lane * 4;
+  const int m = warp % kModes, row0 = (warp / kModes) * RT;   // this warp: mode m, actors row0 .. row0 + RT - 1 of the CTA
+  float *sA = sm + S::offA + row0 * C, *H1 = sm + S::offH1 + (m * GA + row0) * C, *H2 = sm + S::offH2 + (m * GA + row0) * C,
+        *sReg = sm + S::offReg, *sScore = sm + S::offScore, *sCtr = sm + S::offCtr;
+  for (int i = threadIdx.x; i < GA * 32; i += kThreads) {
     const int r = i >> 5, c = (i & 31) * 4;
-    reinterpret_cast<float4*>(sA)[i] = a0 + r < A ? __ldg(reinterpret_cast<const float4*>(actors + (a0 + r) * C + c))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(sm + S::offA)[i] = a0 + r < A ? __ldg(reinterpret_cast<const float4*>(actors + (a0 + r) * C + c))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int i = threadIdx.x; i < kGA * 2; i += kThreads) sCtr[i] = a0 + (i >> 1) < A ? ctrs[(a0 + (i >> 1)) * 2 + (i & 1)] : 0.f;
+  for (int i = threadIdx.x; i < GA * 2; i += kThreads) sCtr[i] = a0 + (i >> 1) < A ? ctrs[(a0 + (i >> 1)) * 2 + (i & 1)] : 0.f;
   __syncthreads();
 
-  float acc[kGA][4];
+  float acc[RT][4];
   // ---- regression head m: LinearRes (layers.py:193-238) then Linear(128, 60) + bias, + actor centre   lanegcn.py:602-612
   {
     const float* h = pack + m * kHead;
     const float *W1 = h, *g1 = W1 + C * C, *b1 = g1 + C, *W2 = b1 + C, *g2 = W2 + C * C, *b2 = g2 + C, *W3 = b2 + C,
                 *bias3 = W3 + C * 64;
-    zero(acc);
-    rows_fma<C>(sA, C, W1, C, co0, acc);
-    gn_rows(acc, g1, b1, nullptr, true, H1, lane);
-    zero(acc);
-    rows_fma<C>(H1, C, W2, C, co0, acc);
-    gn_rows(acc, g2, b2, sA, true, H2, lane);
-    zero(acc);
-    rows_fma<C>(H2, C, W3, 64, co0, acc);
+    zero<RT>(acc);
+    rows_fma<RT, C>(sA, C, W1, C, co0, acc);
+    gn_rows<RT>(acc, g1, b1, nullptr, true, H1, lane);
+    zero<RT>(acc);
+    rows_fma<RT, C>(H1, C, W2, C, co0, acc);
+    gn_rows<RT>(acc, g2, b2, sA, true, H2, lane);
+    zero<RT>(acc);
+    rows_fma<RT, C>(H2, C, W3, 64, co0, acc);
     if (co0 < 64) {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias3 + co0));
 #pragma unroll
-      for (int r = 0; r < kGA; ++r) {   // columns alternate x, y: reg[..., t, 0] += ctr.x, reg[..., t, 1] += ctr.y
-        const float cx = sCtr[2 * r], cy = sCtr[2 * r + 1];
-        *reinterpret_cast<float4*>(sReg + (r * kModes + m) * 64 + co0) =
+      for (int r = 0; r < RT; ++r) {   // columns alternate x, y: reg[..., t, 0] += ctr.x, reg[..., t, 1] += ctr.y
+        const float cx = sCtr[2 * (row0 + r)], cy = sCtr[2 * (row0 + r) + 1];
+        *reinterpret_cast<float4*>(sReg + ((row0 + r) * kModes + m) * 64 + co0) =
             make_float4(acc[r][0] + bb.x + cx, acc[r][1] + bb.y + cy, acc[r][2] + bb.z + cx, acc[r][3] + bb.w + cy);
       }
     }
@@ -142,45 +150,45 @@ k_pred_net(const float* __restrict__ actors, const float* __restrict__ ctrs, con
     const float4 wx = __ldg(reinterpret_cast<const float4*>(Wd0 + co0)), wy = __ldg(reinterpret_cast<const float4*>(Wd0 + C + co0)),
                  b0 = __ldg(reinterpret_cast<const float4*>(bd0 + co0));
 #pragma unroll
-    for (int r = 0; r < kGA; ++r) {
-      const float dx = sCtr[2 * r] - sReg[(r * kModes + m) * 64 + kPred - 2], dy = sCtr[2 * r + 1] - sReg[(r * kModes + m) * 64 + kPred - 1];
+    for (int r = 0; r < RT; ++r) {
+      const float* pr = sReg + ((row0 + r) * kModes + m) * 64;
+      const float dx = sCtr[2 * (row0 + r)] - pr[kPred - 2], dy = sCtr[2 * (row0 + r) + 1] - pr[kPred - 1];
       // same association as addmm(bias, x, W^T): (x0*w0 + x1*w1) + b
       *reinterpret_cast<float4*>(H1 + r * C + co0) =
           relu4(make_float4(fmaf(dy, wy.x, dx * wx.x) + b0.x, fmaf(dy, wy.y, dx * wx.y) + b0.y, fmaf(dy, wy.z, dx * wx.z) + b0.z,
                             fmaf(dy, wy.w, dx * wx.w) + b0.w));
     }
     __syncwarp();
-    zero(acc);
-    rows_fma<C>(H1, C, Wd2, C, co0, acc);
-    gn_rows(acc, gd, bd, nullptr, true, H3, lane);
-    zero(acc);
-    rows_fma<C>(H3, C, Wa, C, co0, acc);                 // columns 0..127 of the 256-wide input: dist
-    rows_fma<C>(sA, C, Wa + C * C, C, co0, acc);         // columns 128..255: the actor feature
-    gn_rows(acc, ga, ba, nullptr, true, H1, lane);       // feats
+    zero<RT>(acc);
+    rows_fma<RT, C>(H1, C, Wd2, C, co0, acc);
+    gn_rows<RT>(acc, gd, bd, nullptr, true, H2, lane);
+    zero<RT>(acc);
+    rows_fma<RT, C>(H2, C, Wa, C, co0, acc);             // columns 0..127 of the 256-wide input: dist
+    rows_fma<RT, C>(sA, C, Wa + C * C, C, co0, acc);     // columns 128..255: the actor feature
+    gn_rows<RT>(acc, ga, ba, nullptr, true, H1, lane);   // feats
   }
   // ---- score head: LinearRes then Linear(128, 1) + bias                                          lanegcn.py:619
   {
     const float* c = pack + kOffCls;
     const float *W1 = c, *g1 = W1 + C * C, *b1 = g1 + C, *W2 = b1 + C, *g2 = W2 + C * C, *b2 = g2 + C, *w3 = b2 + C, *b3 = w3 + C;
-    zero(acc);
-    rows_fma<C>(H1, C, W1, C, co0, acc);
-    gn_rows(acc, g1, b1, nullptr, true, H3, lane);
-    zero(acc);
-    rows_fma<C>(H3, C, W2, C, co0, acc);
-    gn_rows(acc, g2, b2, H1, true, H2, lane);
+    zero<RT>(acc);
+    rows_fma<RT, C>(H1, C, W1, C, co0, acc);
+    gn_rows<RT>(acc, g1, b1, nullptr, true, H2, lane);
+    zero<RT>(acc);
+    rows_fma<RT, C>(H2, C, W2, C, co0, acc);
+    gn_rows<RT>(acc, g2, b2, H1, true, nullptr, lane);   // stays in registers: only the score is needed
     const float4 w = __ldg(reinterpret_cast<const float4*>(w3 + co0));
     const float bias = __ldg(b3);
 #pragma unroll
-    for (int r = 0; r < kGA; ++r) {
-      const float4 v = lds4(H2 + r * C + co0);
-      const float s = warp_sum(fmaf(v.w, w.w, fmaf(v.z, w.z, fmaf(v.y, w.y, v.x * w.x))));
-      if (lane == 0) sScore[r * 8 + m] = s + bias;
+    for (int r = 0; r < RT; ++r) {
+      const float s = warp_sum(fmaf(acc[r][3], w.w, fmaf(acc[r][2], w.z, fmaf(acc[r][1], w.y, acc[r][0] * w.x))));
+      if (lane == 0) sScore[(row0 + r) * 8 + m] = s + bias;
     }
   }
   __syncthreads();
   // ---- descending sort of the 6 scores per actor, trajectories permuted alike (lanegcn.py:621-631), then the world
   //      transform reg . rot[scene] + orig[scene] (lanegcn.py:145-150)
-  for (int r = m; r < kGA; r += kModes) {
+  for (int r = warp; r < GA; r += 2 * kModes) {
     const int64_t a = a0 + r;
     if (a >= A) continue;
     float s[kModes];
@@ -286,12 +294,40 @@ extern "C" int lgcn_pred_net(const float* actors, const float* actor_ctrs, const
   if (n_actors == 0) return 0;
   LGCN_CHECK_ARG(actors && actor_ctrs && wpack && cls && reg, "pred_net: NULL argument");
   LGCN_CHECK_ARG(!rot || (orig && actor_off), "pred_net: rot without orig / actor_off");
-  int dev = 0;
+  int dev = 0, sms = 148;
   LGCN_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && g_attr[dev].exchange(1) == 0)
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  k_pred_net<<<lgcn_cdiv(n_actors, kGA), kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-      actors, actor_ctrs, actor_off, n_scenes, rot, orig, wpack, cls, reg, n_actors, n_actors_dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  if (dev >= 0 && dev < 64 && g_attr[dev].exchange(1) == 0) {
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::floats * 4));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<6>::floats * 4));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<8>::floats * 4));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<10>::floats * 4));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<12>::floats * 4));
+  }
+  // actors per CTA (2 RT): a warp's serial work grows with RT and the CTAs run one per SM in waves, so pick the group
+  // size with the smallest waves x RT (for 2,560 actors on 148 SMs: 20 actors per CTA = 128 CTAs = one wave)
+  int best = 4;
+  int64_t best_cost = -1;
+  for (int rt : {4, 6, 8, 10, 12}) {
+    const int64_t ctas = (n_actors + 2 * rt - 1) / (2 * rt), cost = ((ctas + sms - 1) / sms) * rt;
+    if (best_cost < 0 || cost < best_cost) {
+      best = rt;
+      best_cost = cost;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = lgcn_cdiv(n_actors, 2 * best);
+#define LGCN_PRED(RT_)                                                                                                  \
+  k_pred_net<RT_><<<grid, kThreads, Smem<RT_>::floats * 4, st>>>(actors, actor_ctrs, actor_off, n_scenes, rot, orig, wpack, \
+                                                                 cls, reg, n_actors, n_actors_dev)
+  switch (best) {
+    case 4: LGCN_PRED(4); break;
+    case 6: LGCN_PRED(6); break;
+    case 8: LGCN_PRED(8); break;
+    case 10: LGCN_PRED(10); break;
+    default: LGCN_PRED(12); break;
+  }
+#undef LGCN_PRED
   LGCN_LAUNCH_OK();
   return 0;
 }

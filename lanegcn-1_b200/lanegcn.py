@@ -135,10 +135,11 @@ class _Workspace:
 _SIDE_STREAMS: Dict = {}
 
 
-def _side_stream(device, tag: str = "side"):
+def _side_stream(device, tag: str = "side", priority: int = 0):
+    """Per-device helper streams.  ``priority`` -1 = high (CUDA: lower number = higher priority; default streams are 0)."""
     key = (str(device), tag)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=priority)
     return _SIDE_STREAMS[key]
 
 
@@ -1312,7 +1313,10 @@ class Net(nn.Module):
                     torch.cuda.synchronize(dev)
                     n0 = lib.lgcn_launch_count()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    # captured on a HIGH-priority stream: the map branch (many small, dependent kernels, then the
+                    # SM-filling LaneConv kernels) wins the block scheduler over the ActorNet branch (default priority,
+                    # 1,280 long CTAs that would otherwise occupy every SM first and serialise the two branches)
+                    with torch.cuda.graph(g, stream=_side_stream(dev, "capture", priority=-1)):
                         self._run_slot(slot, fw, b.n_nodes, b.n_actors)
                     slot.graph, slot.weights_version = g, fw.ptrs
                     slot.graph_kernels = int(lib.lgcn_launch_count() - n0)
