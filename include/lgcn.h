@@ -69,6 +69,22 @@ int lgcn_prof_collect(double* h_ms_by_kind, int64_t* h_launches_by_kind);
 int lgcn_pack_host(const void* const* h_srcs, const int64_t* h_nbytes, int64_t n, void* h_dst, int64_t dst_bytes,
                    int n_threads);
 
+/* Batch assembly from PACKED SCENES: one contiguous host blob per sample, made once from the preprocessed-pickle schema
+ * (preprocess_data.py:78-95; lanegcn.pack_scene):
+ *   int64 header[8 + n_kv] = {magic "LGCNSCN1", n_nodes, n_actors, n_scales, idx_bytes, n_index, 0, 0, seg_len[n_kv]}
+ *                            with n_kv = 2 (2 n_scales + 2): entries of pre0.u, pre0.v, suc0.u, ..., left.u, .., right.v
+ *   float arena  ctrs[2N] feats[2N] turn[2N] control[N] intersect[N] actor_feats[60A] actor_ctrs[2A] rot[4] orig[2]
+ *   index arena  the n_kv segments back to back (idx_bytes per entry)
+ * Writes the four staging buffers of lgcn_forward in the CAPACITY layout of LgcnForwardArgs (host memory, normally
+ * pinned; each then needs ONE H2D copy):
+ *   h_fl   float regions at offsets cumsum(2Nc, 2Nc, 2Nc, Nc, Nc, 60Ac, 2Ac, 4Bc, 2Bc)   (Nc/Ac/Bc = capacities)
+ *   h_idx  local_idx;   h_t64 = segs (2 n_kv Bc + 1);   h_t32 = node_off[Bc+1] | actor_off[Bc+1] | dims[4]
+ * Replaces collate_fn + utils.gpu + utils.to_long + the offset/cat loops (data.py:555-561, utils.py:74-96,
+ * lanegcn.py:171-209) for host inputs.  Host-only, n_threads copy threads.                                       */
+int lgcn_stage_scenes(const void* const* h_blobs, int n_scenes, int64_t cap_nodes, int64_t cap_actors, int64_t cap_index,
+                      int cap_scenes, int n_scales, int idx_bytes, float* h_fl, void* h_idx, int64_t* h_t64,
+                      int32_t* h_t32, int n_threads);
+
 /* ------------------------------------------------------------------ graph batching
  * replaces utils.to_long (utils.py:88-96) + the offset/cat loops of graph_gather (lanegcn.py:191-208).
  * `local` holds S segments of scene-local indices (idx_bytes = 2, 4 or 8: int16/int32/int64) laid out

@@ -568,6 +568,60 @@ def _release_pinned():
         _PENDING_PINNED.clear()
 
 
+# --------------------------------------------------------------------------- packed scenes (host data path)
+class PackedScene:
+    """One sample of the preprocessed-pickle schema (preprocess_data.py:78-95; what ArgoDataset.__getitem__ returns,
+    data.py:67-71) as ONE contiguous host blob (layout: include/lgcn.h, lgcn_stage_scenes).  Made once per sample
+    (``pack_scene``: in the Dataset / DataLoader worker), so that staging a batch is B blobs handled in C instead of
+    ~40 tensors per scene walked in Python (the reference: one cudaMemcpyAsync per tensor, utils.py:74-85)."""
+
+    __slots__ = ("blob", "ptr", "n_nodes", "n_actors", "n_index", "idx_bytes", "n_scales")
+    MAGIC = 0x314E43534E43474C   # "LGCNSCN1"
+
+
+def pack_scene(sample: dict) -> PackedScene:
+    """Scene dict (numpy arrays or CPU tensors; keys feats, ctrs, rot, orig, graph{ctrs, feats, turn, control, intersect,
+    pre, suc, left, right}) -> PackedScene."""
+    asnp = lambda x: x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)  # noqa: E731
+    g = sample["graph"]
+    n, a = int(g["num_nodes"]), len(sample["feats"])
+    fl = [g["ctrs"], g["feats"], g["turn"], g["control"], g["intersect"], sample["feats"], sample["ctrs"], sample["rot"],
+          sample["orig"]]
+    fl = [np.ascontiguousarray(asnp(x), np.float32).reshape(-1) for x in fl]
+    want = [2 * n, 2 * n, 2 * n, n, n, 60 * a, 2 * a, 4, 2]
+    if [x.size for x in fl] != want:
+        raise RuntimeError(f"lanegcn_b200: pack_scene: unexpected array sizes {[x.size for x in fl]} (expected {want})")
+    S = len(g["pre"])
+    idx = []
+    for k1, sc in _edge_names(S):
+        d = g[k1] if sc is None else g[k1][sc]
+        for k2 in ("u", "v"):
+            t = asnp(d[k2])
+            idx.append(t.reshape(-1) if t.ndim else t.reshape(0))   # 0-dim: an empty array collapsed (lanegcn.py:204-207)
+    dt = idx[0].dtype
+    if any(x.dtype != dt for x in idx) or dt not in (np.int16, np.int32, np.int64):
+        dt = np.dtype(np.int64)
+    idx = [np.ascontiguousarray(x, dt) for x in idx]
+    n_index = sum(x.size for x in idx)
+    header = np.array([PackedScene.MAGIC, n, a, S, dt.itemsize, n_index, 0, 0] + [x.size for x in idx], np.int64)
+    raw = b"".join([header.tobytes()] + [x.tobytes() for x in fl] + [x.tobytes() for x in idx])
+    raw += b"\0" * (-len(raw) % 8)
+    p = PackedScene()
+    p.blob = np.frombuffer(bytearray(raw), np.uint8)   # owns its memory, 8-byte aligned
+    p.ptr = p.blob.ctypes.data
+    p.n_nodes, p.n_actors, p.n_index, p.idx_bytes, p.n_scales = n, a, n_index, dt.itemsize, S
+    return p
+
+
+def pack_batch(data: Dict) -> Dict:
+    """Attach ``data["_packed"]`` (one PackedScene per sample of a collated batch, data.py:555-561).  Net.stage then
+    takes the C staging path; the dict's own tensors are no longer read."""
+    B = len(data["feats"])
+    data["_packed"] = [pack_scene({"feats": data["feats"][i], "ctrs": data["ctrs"][i], "rot": data["rot"][i],
+                                   "orig": data["orig"][i], "graph": data["graph"][i]}) for i in range(B)]
+    return data
+
+
 # --------------------------------------------------------------------------- Att pair lists
 class PairList:
     """hi/wi (int32) + destination rowptr for one (agents, contexts, threshold) triple."""
@@ -1058,10 +1112,61 @@ class Net(nn.Module):
     def stage(self, data: Dict) -> DeviceBatch:
         """Host packing + H2D of one collated batch (what utils.gpu does tensor by tensor, utils.py:74-85): every
         float of the batch travels in ONE pinned arena, the edge indices in a second, two small integer tables."""
-        if self.one_call_path() and not data["feats"][0].is_cuda and sum(len(x) for x in data["feats"]) > 0 \
-                and sum(int(g["num_nodes"]) for g in data["graph"]) > 0:
-            return self._stage_slot(data)
+        if self.one_call_path():
+            packed = data.get("_packed")
+            if packed is not None and len({(p.idx_bytes, p.n_scales) for p in packed}) == 1 \
+                    and sum(p.n_actors for p in packed) > 0 and sum(p.n_nodes for p in packed) > 0:
+                return self._stage_packed(data, packed)
+            if not data["feats"][0].is_cuda and sum(len(x) for x in data["feats"]) > 0 \
+                    and sum(int(g["num_nodes"]) for g in data["graph"]) > 0:
+                return self._stage_slot(data)
         return self._stage_modules(data)
+
+    def _take_slot(self, dev, caps: "FE.Caps"):
+        bucket = self._buckets.get((str(dev), caps))
+        if bucket is None:
+            while len(self._buckets) >= MAX_BUCKETS:           # oldest first (dicts keep insertion order)
+                self._buckets.pop(next(iter(self._buckets)))
+            with torch.cuda.device(dev):
+                bucket = self._buckets[(str(dev), caps)] = FE.Bucket(caps, dev, self.config, KEEP_PAIR_QUIRK)
+        return bucket.next_slot()
+
+    def _stage_packed(self, data: Dict, packed: List[PackedScene]) -> DeviceBatch:
+        """Staging from packed scenes: ONE C call assembles the four staging buffers in the bucket's capacity layout
+        (lgcn_stage_scenes), four H2D copies follow."""
+        dev, lib = self._device(), _C.lib()
+        B = len(packed)
+        node_sizes, sizes = [p.n_nodes for p in packed], [p.n_actors for p in packed]
+        N, A, total = sum(node_sizes), sum(sizes), sum(p.n_index for p in packed)
+        isz, S = packed[0].idx_bytes, packed[0].n_scales
+        cap_a = FE.round_cap(A)
+        caps = FE.Caps((FE.round_cap(N, 128), cap_a, FE.round_cap(total + (total & 1), 1024), FE.round_cap(B, 1),
+                        *FE.pair_caps(node_sizes, sizes, self._pair_learned, cap_a), isz, S))
+        slot = self._take_slot(dev, caps)
+        b = DeviceBatch()
+        b.slot, b.sizes, b.n_nodes, b.n_actors, b.data = slot, sizes, N, A, data
+        with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev, "copy")):
+            copy = torch.cuda.current_stream()
+            if slot.done is not None:
+                copy.wait_event(slot.done)       # the previous forward on this slot has read its inputs
+            bufs = []
+            for tag, t in (("pk_fl", slot.fl), ("pk_idx", slot.local), ("pk_t64", slot.t64), ("pk_t32", slot.t32)):
+                ring, i, buf = _PinnedPool.take(tag, t.numel() * t.element_size())
+                _PENDING_PINNED.append((ring, i))
+                bufs.append(buf[: t.numel() * t.element_size()].view(t.dtype))
+            ptrs = (ctypes.c_void_p * B)(*[p.ptr for p in packed])
+            _C.check(lib.lgcn_stage_scenes(ptrs, B, caps.nodes, caps.actors, caps.index, caps.scenes, S, isz,
+                                           bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(),
+                                           _PACK_THREADS), "stage_scenes")
+            used = [slot.fl.numel(), max(total, 1), slot.t64.numel(), slot.t32.numel()]
+            for t, h, n in zip((slot.fl, slot.local, slot.t64, slot.t32), bufs, used):
+                t[:n].copy_(h[:n], non_blocking=True)
+            _release_pinned()
+            b.h2d_bytes = sum(n * t.element_size() for t, n in zip((slot.fl, slot.local, slot.t64, slot.t32), used))
+            b.ready = torch.cuda.Event()
+            b.ready.record()
+        b.actor_ctrs = scene_list(slot.actor_ctrs[:A], sizes, slot.actor_off[: B + 1], lazy=True)
+        return b
 
     def _stage_slot(self, data: Dict) -> DeviceBatch:
         dev = self._device()
@@ -1092,13 +1197,7 @@ class Net(nn.Module):
         cap_a = FE.round_cap(A)
         caps = FE.Caps((FE.round_cap(N, 128), cap_a, FE.round_cap(total + (total & 1), 1024), FE.round_cap(B, 1),
                         *FE.pair_caps(node_sizes, sizes, self._pair_learned, cap_a), isz, S))
-        bucket = self._buckets.get((str(dev), caps))
-        if bucket is None:
-            while len(self._buckets) >= MAX_BUCKETS:           # oldest first (dicts keep insertion order)
-                self._buckets.pop(next(iter(self._buckets)))
-            with torch.cuda.device(dev):
-                bucket = self._buckets[(str(dev), caps)] = FE.Bucket(caps, dev, self.config, KEEP_PAIR_QUIRK)
-        slot = bucket.next_slot()
+        slot = self._take_slot(dev, caps)
         Bc = caps.scenes
         b = DeviceBatch()
         b.slot, b.sizes, b.n_nodes, b.n_actors, b.data = slot, sizes, N, A, data

@@ -230,3 +230,18 @@ def test_pred_net_kernel_vs_oracle(cuda, lib, net, n):
     want_w = torch.cat([torch.matmul(r, rot[i]) + orig[i].view(1, 1, 1, -1) for i, r in enumerate(want["reg"])])
     assert_close(reg, want_w, "reg (world)")
     assert torch.equal(cls, torch.cat(got["cls"]))
+
+
+def test_packed_scene_staging_equals_dict_staging(cuda, lib, net):
+    """Net.stage from packed scenes (lgcn_stage_scenes: one C call + 4 H2D copies) == Net.stage from the dict of lists."""
+    scenes = synth.make_scenes(3, "small", seed0=31) + synth.make_scenes(2, "tiny", seed0=32)
+    want = net(synth.collate(scenes))
+    data = L.pack_batch(synth.collate(scenes))
+    b = net.stage(data)
+    assert b.slot is not None and b.h2d_bytes > 0
+    got = net(data)
+    for k in ("cls", "reg"):
+        assert [len(x) for x in got[k]] == [len(x) for x in want[k]]
+        assert torch.equal(torch.cat(got[k]), torch.cat(want[k]))
+    host = list(L.prefetch_forward(net, iter([data, data, data]), to_host=True))
+    assert len(host) == 3 and all(torch.equal(torch.cat(h["reg"]), torch.cat(want["reg"]).cpu()) for h in host)

@@ -121,3 +121,48 @@ def test_shard_and_gather_gloo(world):
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_stage_scenes_matches_reference_batching(lib):
+    """lgcn_stage_scenes (packed scenes -> the four staging buffers in capacity layout) against a numpy restatement of
+    collate + graph_gather's concatenation order (data.py:555-561, lanegcn.py:171-209), with padded scene slots."""
+    import ctypes
+
+    from lanegcn_b200 import _C, forward_engine as FE, lanegcn as L, synth
+
+    scenes = synth.make_scenes(3, "tiny", seed0=1) + synth.make_scenes(2, "small", seed0=5)
+    data = L.pack_batch(synth.collate(scenes))
+    packed = data["_packed"]
+    B, S, n_kv = len(packed), 6, 28
+    N, A, tot = sum(p.n_nodes for p in packed), sum(p.n_actors for p in packed), sum(p.n_index for p in packed)
+    Nc, Ac, Ic, Bc = FE.round_cap(N, 128), FE.round_cap(A), FE.round_cap(tot, 1024), 7
+    off = np.cumsum([0, 2 * Nc, 2 * Nc, 2 * Nc, Nc, Nc, 60 * Ac, 2 * Ac, 4 * Bc, 2 * Bc])
+    fl, idx = np.full(off[-1], np.nan, np.float32), np.full(Ic, -7, np.int16)
+    t64, t32 = np.zeros(2 * n_kv * Bc + 1, np.int64), np.zeros(2 * (Bc + 1) + 4, np.int32)
+    ptrs = (ctypes.c_void_p * B)(*[p.ptr for p in packed])
+    _C.check(lib.lgcn_stage_scenes(ptrs, B, Nc, Ac, Ic, Bc, S, 2, fl.ctypes.data, idx.ctypes.data, t64.ctypes.data,
+                                   t32.ctypes.data, 4))
+    g = data["graph"]
+    for r, (key, k) in enumerate([("ctrs", 2), ("feats", 2), ("turn", 2), ("control", 1), ("intersect", 1)]):
+        assert np.array_equal(fl[off[r]:off[r] + k * N], np.concatenate([x[key].numpy().ravel() for x in g])), key
+    for r, (key, k) in enumerate([("feats", 60 * A), ("ctrs", 2 * A), ("rot", 4 * B), ("orig", 2 * B)]):
+        assert np.array_equal(fl[off[5 + r]:off[5 + r] + k], np.concatenate([x.numpy().ravel() for x in data[key]])), key
+    locs = []
+    for k1, sc in L._edge_names(S):
+        src = [x[k1] for x in g] if sc is None else [x[k1][sc] for x in g]
+        for k2 in ("u", "v"):
+            locs += [d[k2].numpy() for d in src]
+    assert np.array_equal(idx[:tot], np.concatenate(locs))
+    lens = np.zeros((n_kv, Bc), np.int64)
+    lens[:, :B] = np.array([len(x) for x in locs]).reshape(n_kv, B)
+    assert np.array_equal(t64[:n_kv * Bc + 1], np.concatenate(([0], np.cumsum(lens.ravel()))))
+    noff, aoff = np.full(Bc + 1, N), np.full(Bc + 1, A)
+    noff[:B + 1] = np.concatenate(([0], np.cumsum([p.n_nodes for p in packed])))
+    aoff[:B + 1] = np.concatenate(([0], np.cumsum([p.n_actors for p in packed])))
+    assert np.array_equal(t64[n_kv * Bc + 1:], np.tile(noff[:-1], n_kv))
+    assert np.array_equal(t32, np.concatenate((noff, aoff, [N, A, 0, 0])).astype(np.int32))
+    # capacity violations are errors, not overruns
+    assert lib.lgcn_stage_scenes(ptrs, B, N - 1, Ac, Ic, Bc, S, 2, fl.ctypes.data, idx.ctypes.data, t64.ctypes.data,
+                                 t32.ctypes.data, 1) != 0
+    assert lib.lgcn_stage_scenes(ptrs, B, Nc, Ac, Ic, Bc, S, 4, fl.ctypes.data, idx.ctypes.data, t64.ctypes.data,
+                                 t32.ctypes.data, 1) != 0
