@@ -260,7 +260,7 @@ extern "C" int lgcn_laneconv_stack_planned(float* feat, void* plan, int64_t n_ed
   float* w_hi = (float*)((char*)xa + lgcn_laneconv_fused_aux_bytes(n_edges));
   float* w_lo = (float*)((char*)w_hi + lgcn_align_up(LGCN_MAX_PLANNED_BLOCKS * per * 4, 1024));
   // the whole pack (weights and, harmlessly, the norm vectors between them) is split by one launch
-  if (int rc = lgcn_split_tf32(wpack, w_hi, w_lo, (int64_t)n_blocks * per, st)) return rc;
+  if (int rc = lgcn_split_fused(wpack, w_hi, w_lo, (int64_t)n_blocks * per, st)) return rc;
   return lgcn_laneconv_stack_presplit(feat, other, xa, plan, n_edges, n_keys, n_blocks, wpack, w_hi, w_lo, n_nodes,
                                       nullptr, st);
 #else

@@ -134,6 +134,8 @@ struct LgcnSplitList {
   int n_blocks;
 };
 int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st);
+// hi / cross images of a flat run of 128-float rows for the aggregate-first kernel (n floats, n % 128 == 0)
+int lgcn_split_fused(const float* w, float* hi, float* lo, int64_t n, cudaStream_t st);
 int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n_nodes, const int32_t* n_dev,
                                int64_t n_edges, int n_keys, const float* w_hi, const float* w_lo, const float* gn,
                                float* xa, int chain, cudaStream_t st);

@@ -144,8 +144,8 @@ extern "C" int lgcn_forward_prepare(const LgcnForwardWeights* w, int n_scales, v
     one.ldw[0] = ldw[b];
     if (int rc = lgcn_split_blocks_many(one, base + hi[b], base + lo[b], st)) return rc;
   }
-  if (int rc = lgcn_split_tf32(w->map_fuse, base + p.map_hi, base + p.map_lo, stack, st)) return rc;
-  if (int rc = lgcn_split_tf32(w->m2m_fuse, base + p.m2m_hi, base + p.m2m_lo, stack, st)) return rc;
+  if (int rc = lgcn_split_fused(w->map_fuse, base + p.map_hi, base + p.map_lo, stack, st)) return rc;
+  if (int rc = lgcn_split_fused(w->m2m_fuse, base + p.m2m_hi, base + p.m2m_lo, stack, st)) return rc;
   for (int i = 0; i < 6; ++i) {
     LGCN_CHECK_ARG(w->att[i], "forward_prepare: NULL att[%d]", i);
     if (int rc = lgcn_att_split_weights(w->att[i], base + p.att_hi[i], base + p.att_lo[i], st)) return rc;

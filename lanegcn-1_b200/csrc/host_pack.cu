@@ -132,12 +132,16 @@ extern "C" int lgcn_stage_scenes(const void* const* h_blobs, int n_scenes, int64
       }
     }
   };
-  if (n_threads <= 1 || B < 4) {
+  // a thread costs ~30 us to start: one per ~2 MB of payload
+  const int64_t payload = (8 * N + 62 * A + 6 * B) * 4 + run * idx_bytes;
+  int nt = (int)(payload >> 21);
+  nt = nt < n_threads ? nt : n_threads;
+  nt = nt < B ? nt : (int)B;
+  if (nt <= 1) {
     work(0, B);
     return 0;
   }
   std::vector<std::thread> pool;
-  const int nt = n_threads < B ? n_threads : (int)B;
   for (int t = 0; t < nt; ++t) pool.emplace_back(work, B * t / nt, B * (t + 1) / nt);
   for (auto& th : pool) th.join();
   return 0;

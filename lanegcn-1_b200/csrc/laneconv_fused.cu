@@ -64,6 +64,32 @@ constexpr int kSmemTotal = kSmemBar + 256;
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 1;
 constexpr uint32_t kIdesc = idesc_tf32(128, 128);
+// Cross terms on the 16-bit tensor path (2x the tf32 rate): D_cross += [a_lo | a] . [w | w_lo]^T over a K = 64 chunk per
+// stage (4 MMAs of K = 16 instead of 8 tf32 MMAs; a stage = 512 tensor cycles instead of 768); main (tf32(a) . tf32(w)) is
+// unchanged.  LGCN_BF16_CROSS selects the 16-bit format:
+//   0  tf32 cross terms (the 3xTF32 form of round 1)
+//   1  bf16: fp32 range, but 8-bit mantissas put 2^-20 |a w| per term into the sum — measured 1.4x the north-star
+//      tolerance on the batch-32 forward (profiles/r2_cross_terms.md), so NOT used
+//   2  fp16 with the lo operands scaled by 2^11 (a_lo 2^11 ~ |a|, w_lo 2^11 ~ |w|: well inside fp16's range; the cross
+//      accumulator then holds 2^11 x the cross sum and the drain multiplies by 2^-11, exactly): 10-bit mantissas, i.e.
+//      the SAME rounding as tf32 cross terms.  Operands beyond fp16's range saturate at +-65504 (cvt.satfinite: the cross
+//      term of such an element degrades to plain-TF32 accuracy instead of producing inf).
+// Measured on the batch-128 graph (tools/ablate_fused.py, us per block): 519 (mode 0), 484 (mode 1), 497 (mode 2): the
+// kernel is bound by the producer / barrier hand-off (355 us with every MMA, load and conversion switched off), not by
+// the tensor pipe, so a third fewer tensor cycles buy 4-7 %.  Mode 0 stays the default: identical arithmetic to the
+// split path and no range caveat; modes 1 / 2 are kept for the day the A feed is faster (-DLGCN_BF16_CROSS=2).
+#ifndef LGCN_BF16_CROSS
+#define LGCN_BF16_CROSS 0
+#endif
+#if LGCN_BF16_CROSS == 2
+constexpr uint32_t kIdescX = idesc_f16(128, 128);
+constexpr float kLoScale = 2048.0f, kCrossUnscale = 1.0f / 2048.0f;
+#define LGCN_PACK16(hi, lo) pack_f16(hi, lo)
+#else
+constexpr uint32_t kIdescX = idesc_bf16(128, 128);
+constexpr float kLoScale = 1.0f, kCrossUnscale = 1.0f;
+#define LGCN_PACK16(hi, lo) pack_bf16(hi, lo)
+#endif
 constexpr uint32_t kColMain = 256, kColCross = 384;
 // The tensor core truncates the fp32 accumulator toward zero once per MMA instruction (-1.3e-8 relative each, see
 // gemm_tc.cu), so a 240-instruction hi.hi chain (15 keys x 16 k-steps) would carry a 3e-6 bias.  The main accumulator
@@ -202,7 +228,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                 : "memory");
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                ::"r"(dst + kWStageBytes / 2), "l"(reinterpret_cast<uint64_t>(&wlo_map)), "r"(bar), "r"(kc * 32), "r"(kk * 128)
+                ::"r"(dst + kWStageBytes / 2), "l"(reinterpret_cast<uint64_t>(&wlo_map)), "r"(bar),
+                  "r"(kc * (LGCN_BF16_CROSS ? 64 : 32)), "r"(kk * 128)
                 : "memory");
             }
           }
@@ -266,8 +293,12 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
             if (kc == 0 && late_wait) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
+#if LGCN_BF16_CROSS
+                umma_bf16_ts(d_cross, a_lo + 8 * j, umma_desc(w_lo + j * 32), kIdescX, 1u);
+#else
                 umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, 1u);
                 umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
+#endif
               }
               LGCN_FUSED_WAIT(bar_acc_empty, (acc_uses & 1) ^ 1);  // the producers have added main to their sums
               ++acc_uses;
@@ -279,8 +310,13 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
               for (int j = 0; j < 4; ++j) {
                 if (dbg & 4) break;
                 const bool k0 = kc == 0 && j == 0;
+#if LGCN_BF16_CROSS
+                // a_lo / w_lo name the CROSS operands here: [a_lo | a] (32 TMEM columns of bf16 pairs), [w | w_lo] (bf16 tile)
+                umma_bf16_ts(d_cross, a_lo + 8 * j, umma_desc(w_lo + j * 32), kIdescX, (fresh_all && k0) ? 0u : 1u);
+#else
                 umma_tf32_ts(d_cross, a_lo + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_all && k0) ? 0u : 1u);
                 umma_tf32_ts(d_cross, a_hi + 8 * j, umma_desc(w_lo + j * 32), kIdesc, 1u);
+#endif
                 umma_tf32_ts(d_main, a_hi + 8 * j, umma_desc(w_hi + j * 32), kIdesc, (fresh_main && k0) ? 0u : 1u);
               }
             }
@@ -385,6 +421,29 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     // 16 floats -> hi/lo -> TMEM columns [c0, c0+16) (hi) and [c0+32, c0+48) (lo) of A stage `as`; eight columns per
     // tcgen05.st keeps the live temporaries at 16 registers
     auto put16 = [&](const float4(&x)[4], int c0) {
+#if LGCN_BF16_CROSS
+      // hi = tf32(x) -> columns [c0, c0+16); cross operand (two bf16 per column, k even in the low half):
+      // x - hi -> columns 32 + [c0/2, c0/2 + 8),  x itself -> columns 48 + [c0/2, c0/2 + 8)
+      uint32_t lp[8], xp[8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t hi[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 y = x[2 * g + c];
+          const float h0 = rna(y.x), h1 = rna(y.y), h2 = rna(y.z), h3 = rna(y.w);
+          hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+          hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+          lp[4 * g + 2 * c] = LGCN_PACK16((y.y - h1) * kLoScale, (y.x - h0) * kLoScale);
+          lp[4 * g + 2 * c + 1] = LGCN_PACK16((y.w - h3) * kLoScale, (y.z - h2) * kLoScale);
+          xp[4 * g + 2 * c] = LGCN_PACK16(y.y, y.x);
+          xp[4 * g + 2 * c + 1] = LGCN_PACK16(y.w, y.z);
+        }
+        TMEM_ST8(t_lane + as * 64 + c0 + 8 * g, hi, 0);
+      }
+      TMEM_ST8(t_lane + as * 64 + 32 + (c0 >> 1), lp, 0);
+      TMEM_ST8(t_lane + as * 64 + 48 + (c0 >> 1), xp, 0);
+#else
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         uint32_t hi[8], lo[8];
@@ -400,6 +459,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         TMEM_ST8(t_lane + as * 64 + c0 + 8 * g, hi, 0);
         TMEM_ST8(t_lane + as * 64 + 32 + c0 + 8 * g, lo, 0);
       }
+#endif
     };
     auto stage_begin = [&]() {
       LGCN_FUSED_WAIT(bar_empty + 8 * as, a_phase ^ 1);
@@ -462,7 +522,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float y = __uint_as_float(v[c]) + __uint_as_float(x[c]);
+          const float y = LGCN_BF16_CROSS == 2 ? fmaf(__uint_as_float(x[c]), kCrossUnscale, __uint_as_float(v[c]))
+                                               : __uint_as_float(v[c]) + __uint_as_float(x[c]);
           f[g * 16 + c] = add ? f[g * 16 + c] + y : y;
         }
       }
@@ -852,33 +913,47 @@ extern "C" int lgcn_debug_timeline(long long* device_buffer) {
 // ------------------------------------------------------------------ linear mode: lgcn_linear128 on this kernel
 namespace {
 // W [128, n_src*128] (row stride ldw) -> hi / lo blocks [n_src*128, 128]: block k, row n = W[n, 128k .. 128k+127]
+// Weight images of the kernel: hi = tf32(w) as fp32 [row][128], and the CROSS image x (bf16, [row][4 chunks][64]):
+// per 32-float K-chunk kc of a row, 32 x bf16(w) followed by 32 x bf16(w - tf32(w)) — the B operand of the K = 64 bf16
+// cross MMA chain.  (With LGCN_BF16_CROSS=0: x is the fp32 lo = tf32(w - hi) image, [row][128].)  Both images of a row
+// have the same byte size (512 B), so `lo` buffers keep their sizes.
+__device__ __forceinline__ void split_store4(float4 x, int row, int c4, float* __restrict__ hi, float* __restrict__ lo) {
+  float4 a;
+  a.x = rna(x.x); a.y = rna(x.y); a.z = rna(x.z); a.w = rna(x.w);
+  reinterpret_cast<float4*>(hi)[(int64_t)row * 32 + c4] = a;
+#if LGCN_BF16_CROSS
+  const int kc = c4 >> 3, j4 = c4 & 7;   // chunk of 32 floats, float4 inside the chunk
+  uint2* xr = reinterpret_cast<uint2*>(lo) + (int64_t)row * 64 + kc * 16;   // 16 uint2 (= 64 bf16) per chunk
+  xr[j4] = make_uint2(LGCN_PACK16(x.y, x.x), LGCN_PACK16(x.w, x.z));
+  xr[8 + j4] = make_uint2(LGCN_PACK16((x.y - a.y) * kLoScale, (x.x - a.x) * kLoScale),
+                          LGCN_PACK16((x.w - a.w) * kLoScale, (x.z - a.z) * kLoScale));
+#else
+  float4 b;
+  b.x = rna(x.x - a.x); b.y = rna(x.y - a.y); b.z = rna(x.z - a.z); b.w = rna(x.w - a.w);
+  reinterpret_cast<float4*>(lo)[(int64_t)row * 32 + c4] = b;
+#endif
+}
+
+// W [128, n_src*128] (row stride ldw) -> images of blocks [n_src*128, 128]: block k, row n = W[n, 128k .. 128k+127]
 __global__ void k_split_blocks(const float* __restrict__ w, int64_t ldw, int n_src, float* __restrict__ hi,
                                float* __restrict__ lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of the output
   if (i >= n_src * 128 * 32) return;
   const int c4 = i & 31, n = (i >> 5) & 127, k = i >> 12;
-  const float4 x = *reinterpret_cast<const float4*>(w + (int64_t)n * ldw + k * 128 + c4 * 4);
-  float4 a, b;
-  a.x = rna(x.x); b.x = rna(x.x - a.x);
-  a.y = rna(x.y); b.y = rna(x.y - a.y);
-  a.z = rna(x.z); b.z = rna(x.z - a.z);
-  a.w = rna(x.w); b.w = rna(x.w - a.w);
-  reinterpret_cast<float4*>(hi)[i] = a;
-  reinterpret_cast<float4*>(lo)[i] = b;
+  split_store4(*reinterpret_cast<const float4*>(w + (int64_t)n * ldw + k * 128 + c4 * 4), i >> 5, c4, hi, lo);
 }
 
 __global__ void k_split_many(const LgcnSplitList l, float* __restrict__ hi, float* __restrict__ lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of the output
   if (i >= l.n_blocks * 128 * 32) return;
   const int c4 = i & 31, n = (i >> 5) & 127, b = i >> 12;
-  const float4 x = *reinterpret_cast<const float4*>(l.p[b] + (int64_t)n * l.ldw[b] + c4 * 4);
-  float4 a, c;
-  a.x = rna(x.x); c.x = rna(x.x - a.x);
-  a.y = rna(x.y); c.y = rna(x.y - a.y);
-  a.z = rna(x.z); c.z = rna(x.z - a.z);
-  a.w = rna(x.w); c.w = rna(x.w - a.w);
-  reinterpret_cast<float4*>(hi)[i] = a;
-  reinterpret_cast<float4*>(lo)[i] = c;
+  split_store4(*reinterpret_cast<const float4*>(l.p[b] + (int64_t)n * l.ldw[b] + c4 * 4), i >> 5, c4, hi, lo);
+}
+
+// a flat run of 128-float rows (a whole LaneConv wpack: the norm vectors between the matrices are split harmlessly)
+__global__ void k_split_rows(const float4* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) split_store4(w[i], (int)(i >> 5), (int)(i & 31), hi, lo);
 }
 
 // Scratch for the split weights of a launch whose caller did not pre-split them (the stand-alone lgcn_linear128 entry
@@ -897,6 +972,14 @@ struct SplitRing {
 SplitRing g_rings[kMaxDevices];
 std::mutex g_ring_mu;
 
+int make_cross_map(CUtensorMap* m, const float* w_x, int64_t rows) {
+#if LGCN_BF16_CROSS
+  return make_map_2d_bf16(m, w_x, 256, rows, 256, 64, 128);    // [rows][4 chunks x 64 bf16], one chunk per box
+#else
+  return make_map_2d(m, w_x, LGCN_C, rows, LGCN_C, 32, 128);
+#endif
+}
+
 int set_fused_attrs() {
   if (!first_use(kFamFused)) return 0;
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
@@ -905,6 +988,15 @@ int set_fused_attrs() {
   return 0;
 }
 }  // namespace
+
+// images of n floats (a multiple of 128) for the aggregate-first kernel (LaneConv stacks)
+int lgcn_split_fused(const float* w, float* hi, float* lo, int64_t n, cudaStream_t st) {
+  LGCN_CHECK_ARG(n % 128 == 0, "split_fused: n %% 128 != 0");
+  if (n == 0) return 0;
+  k_split_rows<<<lgcn_cdiv(n / 4, 256), 256, 0, st>>>((const float4*)w, hi, lo, n / 4);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
 
 int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st) {
   LGCN_CHECK_ARG(l.n_blocks >= 1 && l.n_blocks <= 8, "split_blocks_many: n_blocks %d", l.n_blocks);
@@ -944,7 +1036,7 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, la.out, LGCN_C, la.m, la.ldo)) return rc;
   if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)la.n_src * LGCN_C, LGCN_C, 32, 128)) return rc;
-  if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)la.n_src * LGCN_C, LGCN_C, 32, 128)) return rc;
+  if (int rc = make_cross_map(&mlo, w_lo, (int64_t)la.n_src * LGCN_C)) return rc;
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   for (int k = 0; k < la.n_src; ++k) {
@@ -993,7 +1085,7 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, out, LGCN_C, n_nodes, LGCN_C)) return rc;
   if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
-  if (int rc = make_map_2d(&mlo, w_lo, LGCN_C, (int64_t)nkw * LGCN_C, LGCN_C, 32, 128)) return rc;
+  if (int rc = make_cross_map(&mlo, w_lo, (int64_t)nkw * LGCN_C)) return rc;
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   a.X = x; a.XA = xa; a.tab = v.tab; a.gn = gn; a.M = n_nodes; a.m_dev = n_dev; a.n_keys = n_keys; a.chain = chain; a.dbg = lgcn_debug_get();

@@ -105,6 +105,35 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// D[tmem] (+)= A[tmem: row -> lane, TWO bf16 per 32-bit column (k even in the low half)] . B[smem desc]^T, K = 16
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor, kind::f16 with bf16 operands: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// instruction descriptor, kind::f16 with fp16 operands (format 0), fp32 accumulation
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// {hi, lo} -> two fp16 (round to nearest even, saturating to +-65504 instead of inf): `lo` in the low half
+__device__ __forceinline__ uint32_t pack_f16(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// {hi, lo} -> one 32-bit word of two bf16 (round to nearest even): `lo` in the low half
+__device__ __forceinline__ uint32_t pack_bf16(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -186,6 +215,8 @@ EncodeTiledFn get_encode();
 int make_out_map(CUtensorMap* map, float* out, int64_t cols, int64_t rows, int64_t ldo);
 // generic 2-D fp32 map: [rows, cols] with row stride ld floats, box {box_cols, box_rows}, SWIZZLE_128B
 int make_map_2d(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows);
+// the same over a bf16 tensor (cols / ld / box_cols in bf16 elements)
+int make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows);
 // Per-DEVICE cached state (one process may drive several GPUs: the Python layer keys its workspaces per device and
 // wraps calls in torch.cuda.device(dev)).  num_sms(): SM count of the CURRENT device.  first_use(family): true
 // exactly once per (current device, kernel family) — cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device.

@@ -500,6 +500,7 @@ _DATA_PTR = operator.methodcaller("data_ptr")
 _IS_CONTIG = operator.methodcaller("is_contiguous")
 _DTYPE = operator.attrgetter("dtype")
 _NBYTES = operator.attrgetter("nbytes")
+_VERSION = operator.attrgetter("_version")
 
 
 def _stage_cat(parts: List[Tensor], dev, dtype, tag: str) -> Tensor:
@@ -1020,6 +1021,10 @@ class _ForwardWeights:
         self.prepared = None
         self.struct = _C.ForwardWeights()
         self.key = None
+        self.refs = None        # (parameter dict, name) of every parameter of the Net, collected once
+        self.fast_key = None
+        self.dirty = False      # set by Net.invalidate_packs
+        self.ptrs = None
 
 
 class Net(nn.Module):
@@ -1071,6 +1076,7 @@ class Net(nn.Module):
             if isinstance(wp, _WPack):
                 wp.invalidate()
         for fw in self._fw.values():
+            fw.dirty = True
             for wp in fw.packs.values():
                 wp.invalidate()
         self.actor_net._pp.invalidate()
@@ -1081,6 +1087,14 @@ class Net(nn.Module):
         fw = self._fw.get(str(dev))
         if fw is None:
             fw = self._fw[str(dev)] = _ForwardWeights()
+        # fast check, once per forward: (storage address, version counter) of every parameter of the model; only when
+        # one of them moved are the per-module packs examined (walking the module tree costs ~0.4 ms of host time)
+        if fw.refs is None:
+            fw.refs = [(m._parameters, n) for m in self.modules() for n, v in m._parameters.items() if v is not None]
+        ps = [d[n] for d, n in fw.refs]
+        fast = (tuple(map(_DATA_PTR, ps)), tuple(map(_VERSION, ps)))
+        if fast == fw.fast_key and not fw.dirty:
+            return fw
         mn, lib = self.map_net, _C.lib()
         mlp = lambda seq: (lambda: [(seq[0], "weight"), (seq[0], "bias"), (seq[2].linear, "weight"),  # noqa: E731
                                     (seq[2].norm, "weight"), (seq[2].norm, "bias")])
@@ -1106,6 +1120,7 @@ class Net(nn.Module):
             st.prepared = fw.prepared.data_ptr()
             _C.check(lib.lgcn_forward_prepare(ctypes.byref(st), self.config["num_scales"], _C.stream_ptr()), "forward_prepare")
             fw.key = key
+        fw.fast_key, fw.dirty = fast, False
         return fw
 
     # ------------------------------------------------------------------ staging
@@ -1517,6 +1532,9 @@ def _graph_tensors(g: dict):
                     yield from (t for t in e.values() if torch.is_tensor(t))
 
 
+_NO_OFF = torch.zeros(1, dtype=torch.int32)   # placeholder offsets of host-side result lists (never read)
+
+
 def _cat_of(lst) -> Tensor:
     """The batched tensor behind a per-scene list (no concatenation when it is a SceneList)."""
     if isinstance(lst, SceneList) and lst.cat is not None:
@@ -1560,7 +1578,8 @@ def prefetch_forward(net: "Net", batches, to_host: bool = False, post=None):
             return out if to_host == "defer" else {k: [t.cpu() for t in out[k]] for k in ("cls", "reg")}
         if to_host == "defer":
             return {"cls": cls_h, "reg": reg_h}
-        return {"cls": list(cls_h.split_with_sizes(sizes)), "reg": list(reg_h.split_with_sizes(sizes))}
+        # per-scene lists of views of the pinned results, created on first access
+        return {"cls": scene_list(cls_h, sizes, _NO_OFF, lazy=True), "reg": scene_list(reg_h, sizes, _NO_OFF, lazy=True)}
 
     held = None   # (cls_host, reg_host, sizes, copied event, batch) of the previous batch
     while staged is not None:

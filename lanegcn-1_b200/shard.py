@@ -79,9 +79,17 @@ def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, 
         buf[:n, k:] = reg.reshape(n, -1)
     full = torch.empty(world * plan.max_actors, width, dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(full, buf, group=group)
-    res = {"cls": [], "reg": []}
-    for r, sizes in enumerate(plan.per_rank):
-        part = full[r * plan.max_actors: r * plan.max_actors + sum(sizes)]
-        res["cls"] += list(torch.split(part[:, :k], sizes))
-        res["reg"] += [x.reshape((-1,) + tail) for x in torch.split(part[:, k:], sizes)]
-    return res
+    # compact the ranks' valid rows (2 small copies) and hand out per-scene lists whose views are created on first use
+    # (splitting a 128-scene result into 256 views costs ~0.4 ms of host time per step)
+    from .lanegcn import scene_list
+
+    counts = [sum(s) for s in plan.per_rank]
+    if all(c == plan.max_actors for c in counts):
+        valid = full
+    else:
+        valid = torch.cat([full[r * plan.max_actors: r * plan.max_actors + c] for r, c in enumerate(counts)], 0)
+    sizes = [x for s in plan.per_rank for x in s]
+    cls = valid[:, :k].contiguous()
+    reg = valid[:, k:].contiguous().view((-1,) + tail)
+    off = torch.zeros(1, dtype=torch.int32)
+    return {"cls": scene_list(cls, sizes, off, lazy=True), "reg": scene_list(reg, sizes, off, lazy=True)}
