@@ -8,8 +8,10 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is DEVICE memory unless its name starts with h_.
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises unless
- *     the comment says so.  The library never allocates, frees or retains caller memory: outputs and
- *     workspaces are caller-provided (sizes from the *_workspace_bytes helpers).
+ *     the comment says so.  The library never frees or retains caller memory and does not allocate: outputs and
+ *     workspaces are caller-provided (sizes from the *_workspace_bytes helpers); the single exception is the scratch
+ *     ring of the convenience entry lgcn_linear128 (see lgcn_linear128_ws).  Library state is per device (cached
+ *     function attributes, SM count, that ring); entry points are safe to call from one host thread per GPU.
  *   - return 0 on success, <0 on error; lgcn_last_error() gives the thread-local message.
  *   - feature matrices are row-major fp32 with 128 channels (config n_map = n_actor = 128).
  *   - nn.Linear weights are [out, in] row-major (y = x * W^T), as in the reference state_dict.
@@ -39,28 +41,9 @@ const char* lgcn_last_error(void);
 int lgcn_get_gemm_engine(void);
 int lgcn_set_gemm_engine(int engine);
 
-/* Profiling ablations of the tcgen05 kernels (results become WRONG unless noted; never set in production; returns
- * the previous value): 1 = epilogue skips staging + TMA stores, 2 = epilogue skips the cross-accumulator reads
- * (gemm_tc*.cu), 4 = MMA issuer skips the tcgen05.mma instructions, 8 = producers skip global loads (and, in
- * gemm_tc*.cu, the conversion), 16 = route the multi-block projection through the generic kernel instead of the
- * A-in-TMEM one (results stay right); aggregate-first kernel only: 32 = no A conversion / tcgen05.st,
- * 64 = no accumulator flushes, 128 = no weight TMA, 256 = write the clock timeline (needs a -DLGCN_TIMELINE build,
- * lgcn_debug_timeline), 512 = flush every 5 keys instead of 3 (results stay within tolerance on the goldens but
- * not on the stress case of tools/precision_fused.py); 32768 = one-block Linears on the first-generation k_linear_tc
- * instead of the linear mode of the aggregate-first kernel (results stay right). */
-int lgcn_debug_flags(int flags);
-/* Profiling aid: device buffer [1024][8] of int64 clock stamps filled by CTA 0 of the aggregate-first LaneConv kernel
- * while debug flag 256 is set (tools/timeline_fused.py). */
-int lgcn_debug_timeline(long long* device_buffer);
 /* number of CUDA kernels this library has launched in this process (all entry points) */
 int64_t lgcn_launch_count(void);
-/* Per-kernel timing for the benchmark: while enabled, lgcn_laneconv_stack / lgcn_att_forward bracket their
- * launches with CUDA events on the launching stream.  lgcn_prof_collect SYNCHRONISES on those events, returns
- * summed milliseconds and launch counts per kind (0 wide projection GEMM, 1 LaneConv gather, 2 ctr2 linear,
- * 3 whole Att layer, 4 aggregate-first LaneConv block incl. its multi-source pre-pass; ARRAYS OF 8, the rest
- * reserved) and resets.  lgcn_prof_enable returns the previous state. */
-int lgcn_prof_enable(int on);
-int lgcn_prof_collect(double* h_ms_by_kind, int64_t* h_launches_by_kind);
+/* (profiling / ablation switches live in lgcn_debug.h: they are not part of the product interface) */
 
 /* ------------------------------------------------------------------ host staging
  * Copies n host arrays (h_srcs[i], h_nbytes[i] bytes) back to back into the host arena h_dst (normally pinned
@@ -151,6 +134,17 @@ int lgcn_linear128(const float* a0, const int32_t* idx0, const float* a1, const 
                    const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks, const float* W,
                    int n_out_blocks, const float* gamma, const float* beta, const float* res, int flags,
                    float* out, int64_t ldo, int64_t m, void* stream);
+
+/* The same with a caller-provided scratch buffer of lgcn_linear128_workspace_bytes() bytes for the tf32 images of W
+ * (the tcgen05 engine splits W before the GEMM).  lgcn_linear128 itself is the convenience form: without a workspace it
+ * uses a small scratch ring that the library allocates once per device on first use — the ONE place the library owns
+ * device memory; every fused entry point (lgcn_forward, lgcn_att_forward, lgcn_laneconv_stack*) takes its scratch from
+ * the caller.  The workspace must stay untouched until the call's kernels have run (stream order is enough).       */
+int64_t lgcn_linear128_workspace_bytes(void);
+int lgcn_linear128_ws(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1,
+                      const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks, const float* W,
+                      int n_out_blocks, const float* gamma, const float* beta, const float* res, int flags,
+                      float* out, int64_t ldo, int64_t m, void* workspace, void* stream);
 
 /* h[m,:] = relu(W1[128,2] . x[m] + b1), x[m] = p[ip ? ip[m] : m] - (q ? q[iq ? iq[m] : m] : 0)
  * The nn.Linear(2,128)+ReLU heads of MapNet.input/seg (lanegcn.py:277-286) and Att.dist (:644-648, with

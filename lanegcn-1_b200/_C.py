@@ -13,6 +13,7 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblgcn_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "lgcn.h")
+DEBUG_HEADER_PATH = os.path.join(_HERE, "..", "include", "lgcn_debug.h")
 
 EPI_GN, EPI_RELU1, EPI_RES, EPI_RELU2 = 1, 2, 4, 8
 
@@ -41,6 +42,9 @@ _SIGS = {
     "lgcn_dilate_square": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_linear128": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32,
                               _vp, _i64, _i64, _vp]),
+    "lgcn_linear128_workspace_bytes": (_i64, []),
+    "lgcn_linear128_ws": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32,
+                                 _vp, _i64, _i64, _vp, _vp]),
     "lgcn_mlp2_in": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_mlp4_in": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lgcn_gather_rows_gn_relu": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -100,8 +104,8 @@ _lib = None
 
 
 def header_symbols() -> list:
-    """Function names declared in include/lgcn.h (comments stripped)."""
-    src = open(HEADER_PATH).read()
+    """Function names declared in include/lgcn.h and include/lgcn_debug.h (comments stripped)."""
+    src = open(HEADER_PATH).read() + open(DEBUG_HEADER_PATH).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(lgcn_[a-z0-9_]+)\s*\(", src)))
 

@@ -108,20 +108,46 @@ static int check_linear(const LinearArgs& a) {
   return 0;
 }
 
-extern "C" int lgcn_linear128(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1,
-                              const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks,
-                              const float* W, int n_out_blocks, const float* gamma, const float* beta,
-                              const float* res, int flags, float* out, int64_t ldo, int64_t m, void* stream) {
+static int linear128_impl(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1, const float* a2,
+                          const int32_t* idx2, int n_src, const float* xs, int ks, const float* W, int n_out_blocks,
+                          const float* gamma, const float* beta, const float* res, int flags, float* out, int64_t ldo,
+                          int64_t m, void* workspace, void* stream) {
   LinearArgs a;
+  memset(&a, 0, sizeof(a));
   a.a[0] = a0; a.a[1] = a1; a.a[2] = a2;
   a.idx[0] = idx0; a.idx[1] = idx1; a.idx[2] = idx2;
   a.n_src = n_src; a.xs = xs; a.ks = ks; a.W = W; a.n_out_blocks = n_out_blocks;
   a.gamma = gamma; a.beta = beta; a.res = res; a.flags = flags; a.out = out; a.ldo = ldo; a.m = m;
   a.dbg = g_debug;
-  a.w_hi = a.w_lo = nullptr;
-  a.m_dev = nullptr;
+  a.split_ws = workspace;
   if (check_linear(a)) return -1;
   return lgcn_launch_linear(a, (cudaStream_t)stream);
+}
+
+extern "C" int64_t lgcn_linear128_workspace_bytes(void) {
+#if LGCN_HAVE_TC
+  return lgcn_linear_split_bytes();
+#else
+  return 0;
+#endif
+}
+
+extern "C" int lgcn_linear128_ws(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1,
+                                 const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks,
+                                 const float* W, int n_out_blocks, const float* gamma, const float* beta,
+                                 const float* res, int flags, float* out, int64_t ldo, int64_t m, void* workspace,
+                                 void* stream) {
+  LGCN_CHECK_ARG(workspace || lgcn_get_gemm_engine() == 0, "linear128_ws: NULL workspace");
+  return linear128_impl(a0, idx0, a1, idx1, a2, idx2, n_src, xs, ks, W, n_out_blocks, gamma, beta, res, flags, out, ldo, m,
+                        workspace, stream);
+}
+
+extern "C" int lgcn_linear128(const float* a0, const int32_t* idx0, const float* a1, const int32_t* idx1,
+                              const float* a2, const int32_t* idx2, int n_src, const float* xs, int ks,
+                              const float* W, int n_out_blocks, const float* gamma, const float* beta,
+                              const float* res, int flags, float* out, int64_t ldo, int64_t m, void* stream) {
+  return linear128_impl(a0, idx0, a1, idx1, a2, idx2, n_src, xs, ks, W, n_out_blocks, gamma, beta, res, flags, out, ldo, m,
+                        nullptr, stream);
 }
 
 LinearArgs lgcn_lin1(const float* x, const int32_t* idx, const float* W, const float* gamma, const float* beta,

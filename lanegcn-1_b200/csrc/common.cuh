@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "../../include/lgcn.h"
+#include "../../include/lgcn_debug.h"
 
 #define LGCN_WARP 32
 #define LGCN_GN_EPS 1e-5f
@@ -117,6 +118,9 @@ struct LinearArgs {
   // NULL the tcgen05 path splits W into a scratch slot at launch
   const float* w_hi;
   const float* w_lo;
+  // optional caller-provided scratch for that split (lgcn_linear128_workspace_bytes); without it the tcgen05 path uses
+  // the library's lazily allocated per-device scratch ring (lgcn_linear128 only)
+  void* split_ws;
 };
 int lgcn_debug_get();
 int lgcn_launch_linear_simt(const LinearArgs& a, cudaStream_t st);
@@ -127,6 +131,7 @@ int lgcn_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_
 int lgcn_launch_wide_tc(const LinearArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st);
 int64_t lgcn_laneconv_fused_aux_bytes(int64_t n_edges);
 int lgcn_launch_linear_fused(const LinearArgs& a, cudaStream_t st);
+int64_t lgcn_linear_split_bytes();
 // split up to 8 weight blocks W_b[n, 0..127] = p[b][n * ldw[b] + 0..127] (n < 128) into hi / lo [n_blocks*128, 128]
 struct LgcnSplitList {
   const float* p[8];

@@ -998,6 +998,8 @@ int lgcn_split_fused(const float* w, float* hi, float* lo, int64_t n, cudaStream
   return 0;
 }
 
+int64_t lgcn_linear_split_bytes() { return kSlotFloats * (int64_t)sizeof(float); }
+
 int lgcn_split_blocks_many(const LgcnSplitList& l, float* hi, float* lo, cudaStream_t st) {
   LGCN_CHECK_ARG(l.n_blocks >= 1 && l.n_blocks <= 8, "split_blocks_many: n_blocks %d", l.n_blocks);
   k_split_many<<<lgcn_cdiv(l.n_blocks * 128 * 32, 256), 256, 0, st>>>(l, hi, lo);
@@ -1013,7 +1015,16 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   const float *w_hi = la.w_hi, *w_lo = la.w_lo;
   int slot = -1;
   SplitRing& ring = g_rings[current_device()];
-  if (!w_hi || !w_lo) {   // split W into a scratch slot
+  if ((!w_hi || !w_lo) && la.split_ws) {   // split W into the caller's workspace (stream-ordered reuse is the caller's)
+    float* s_hi = (float*)la.split_ws;
+    float* s_lo = s_hi + kSlotFloats / 2;
+    const int64_t ldw = (int64_t)la.n_src * LGCN_C + la.ks;
+    k_split_blocks<<<lgcn_cdiv(la.n_src * 128 * 32, 256), 256, 0, st>>>(la.W, ldw, la.n_src, s_hi, s_lo);
+    LGCN_LAUNCH_OK();
+    w_hi = s_hi;
+    w_lo = s_lo;
+  }
+  if (!w_hi || !w_lo) {   // split W into a slot of the library's own scratch ring
     std::lock_guard<std::mutex> lock(g_ring_mu);
     if (!ring.buf) {
       LGCN_CUDA_OK(cudaMalloc(&ring.buf, kRing * kSlotFloats * sizeof(float)));

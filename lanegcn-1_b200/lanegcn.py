@@ -143,6 +143,12 @@ def _side_stream(device, tag: str = "side", priority: int = 0):
     return _SIDE_STREAMS[key]
 
 
+def _lin_ws() -> int:
+    """Scratch of lgcn_linear128_ws on the current device (stream-ordered reuse: the calls of a forward share it)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return _Workspace.get(_C.lib().lgcn_linear128_workspace_bytes(), dev, "linear128").data_ptr()
+
+
 def _need_cuda(t: Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"lanegcn_b200: {what} must be a CUDA tensor (there is no CPU path)")
@@ -796,9 +802,9 @@ class MapNet(_LaneConvStack):
         ):
             _C.check(lib.lgcn_mlp2_in(src.data_ptr(), None, None, None, mlp[0].weight.data_ptr(),
                                       mlp[0].bias.data_ptr(), hid.data_ptr(), n, st), "mlp2_in")
-            _C.check(lib.lgcn_linear128(hid.data_ptr(), None, None, None, None, None, 1, None, 0,
+            _C.check(lib.lgcn_linear128_ws(hid.data_ptr(), None, None, None, None, None, 1, None, 0,
                                         mlp[2].linear.weight.data_ptr(), 1, mlp[2].norm.weight.data_ptr(),
-                                        mlp[2].norm.bias.data_ptr(), _C.ptr(res), flags, out.data_ptr(), C_, n,
+                                        mlp[2].norm.bias.data_ptr(), _C.ptr(res), flags, out.data_ptr(), C_, n, _lin_ws(),
                                         st), "linear128")
         feat = self._stack(feat, pg)
         return feat, graph["idcs"], graph["ctrs"]
@@ -903,10 +909,10 @@ class A2M(nn.Module):
         n = feat.shape[0]
         out = torch.empty_like(feat)
         # feat = relu(GN(Linear_132->128(cat(feat, turn, control, intersect))))        lanegcn.py:387-395
-        _C.check(lib.lgcn_linear128(feat.data_ptr(), None, None, None, None, None, 1, pg.meta.data_ptr(), 4,
+        _C.check(lib.lgcn_linear128_ws(feat.data_ptr(), None, None, None, None, None, 1, pg.meta.data_ptr(), 4,
                                     self.meta.linear.weight.data_ptr(), 1, self.meta.norm.weight.data_ptr(),
                                     self.meta.norm.bias.data_ptr(), None, _C.EPI_GN | _C.EPI_RELU1,
-                                    out.data_ptr(), C_, n, _C.stream_ptr()), "linear128(meta)")
+                                    out.data_ptr(), C_, n, _lin_ws(), _C.stream_ptr()), "linear128(meta)")
         feat = out
         pairs = _shared_pairs(graph["idcs"], graph["ctrs"], actor_idcs, actor_ctrs, self.config["actor2map_dist"], pairs)
         for att in self.att:

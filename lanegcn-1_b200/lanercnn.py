@@ -15,7 +15,7 @@ from torch import Tensor, nn
 
 from . import _C
 from .blocks import Linear
-from .lanegcn import (C_, _LaneConvStack, _as_scene_list, _f32c, _need_cuda, _packed_of, _target_device,
+from .lanegcn import (C_, _LaneConvStack, _lin_ws, _as_scene_list, _f32c, _need_cuda, _packed_of, _target_device,
                       build_pair_lists, scene_list)
 
 
@@ -42,10 +42,10 @@ class LaneRoI(_LaneConvStack):
         _need_cuda(feat, "feat")
         feat = _f32c(feat)
         out = torch.empty_like(feat)
-        _C.check(_C.lib().lgcn_linear128(feat.data_ptr(), None, None, None, None, None, 1, None, 0,
+        _C.check(_C.lib().lgcn_linear128_ws(feat.data_ptr(), None, None, None, None, None, 1, None, 0,
                                          self.input.linear.weight.data_ptr(), 1, self.input.norm.weight.data_ptr(),
                                          self.input.norm.bias.data_ptr(), None, _C.EPI_GN | _C.EPI_RELU1,
-                                         out.data_ptr(), C_, feat.shape[0], _C.stream_ptr()), "linear128(LaneRoI.input)")
+                                         out.data_ptr(), C_, feat.shape[0], _lin_ws(), _C.stream_ptr()), "linear128(LaneRoI.input)")
         return self._stack(out, _packed_of(graph))
 
 
@@ -149,8 +149,8 @@ def _scatter_csr(dst: Tensor, src_index: Tensor, n_rows: int, n_src: int):
 
 def _lin(x, w, gamma=None, beta=None, res=None, flags=0, idx=None):
     out = torch.empty(x.shape[0] if idx is None else idx.shape[0], C_, dtype=torch.float32, device=x.device)
-    _C.check(_C.lib().lgcn_linear128(x.data_ptr(), _C.ptr(idx), None, None, None, None, 1, None, 0, w.data_ptr(), 1,
-                                     _C.ptr(gamma), _C.ptr(beta), _C.ptr(res), flags, out.data_ptr(), C_, out.shape[0],
+    _C.check(_C.lib().lgcn_linear128_ws(x.data_ptr(), _C.ptr(idx), None, None, None, None, 1, None, 0, w.data_ptr(), 1,
+                                     _C.ptr(gamma), _C.ptr(beta), _C.ptr(res), flags, out.data_ptr(), C_, out.shape[0], _lin_ws(),
                                      _C.stream_ptr()), "linear128")
     return out
 
@@ -221,9 +221,9 @@ class LanePooling(nn.Module):
                                   dist.data_ptr(), P, st), "mlp4_in")
         c0 = self.ctx[0]
         ctx = torch.empty(P, C_, dtype=torch.float32, device=dist.device)
-        _C.check(lib.lgcn_linear128(context_feat.data_ptr(), pairs.hi.data_ptr(), dist.data_ptr(), None, None, None, 2,
+        _C.check(lib.lgcn_linear128_ws(context_feat.data_ptr(), pairs.hi.data_ptr(), dist.data_ptr(), None, None, None, 2,
                                     None, 0, c0.linear.weight.data_ptr(), 1, c0.norm.weight.data_ptr(),
-                                    c0.norm.bias.data_ptr(), None, _C.EPI_GN | _C.EPI_RELU1, ctx.data_ptr(), C_, P, st),
+                                    c0.norm.bias.data_ptr(), None, _C.EPI_GN | _C.EPI_RELU1, ctx.data_ptr(), C_, P, _lin_ws(), st),
                  "linear128(ctx.0)")
         ctx = _lin(ctx, self.ctx[1].weight)
         t = _lin(target_feat, self.input.weight)
@@ -258,9 +258,9 @@ class Interactor(nn.Module):
                                           (feats, self.seg, a, _C.EPI_GN | _C.EPI_RES | _C.EPI_RELU2, g_in)):
             _C.check(lib.lgcn_mlp2_in(_f32c(src).data_ptr(), None, None, None, mlp[0].weight.data_ptr(),
                                       mlp[0].bias.data_ptr(), hid.data_ptr(), n, st), "mlp2_in")
-            _C.check(lib.lgcn_linear128(hid.data_ptr(), None, None, None, None, None, 1, None, 0,
+            _C.check(lib.lgcn_linear128_ws(hid.data_ptr(), None, None, None, None, None, 1, None, 0,
                                         mlp[2].linear.weight.data_ptr(), 1, mlp[2].norm.weight.data_ptr(),
-                                        mlp[2].norm.bias.data_ptr(), _C.ptr(res), flags, out.data_ptr(), C_, n, st),
+                                        mlp[2].norm.bias.data_ptr(), _C.ptr(res), flags, out.data_ptr(), C_, n, _lin_ws(), st),
                      "linear128")
         graph_feat = self.roi2graph(roi_feat, subgraph, g_in, graph)
         graph_feat = self.global_graph_net(graph_feat, graph)
