@@ -354,7 +354,7 @@ def run_forward(args):
 
     def step_device(staged):
         out = net.forward_device(staged)
-        return shard.gather_outputs(out, plan) if world > 1 else out
+        return shard.gather_outputs(out, plan, lazy=True) if world > 1 else out
 
     def sync_all():
         torch.cuda.synchronize()
@@ -411,8 +411,7 @@ def run_forward(args):
     # ---- N > 1: the NCCL-gathered result against ONE rank's forward of the whole batch
     gather_verified = None
     if world > 1:
-        got_cls = torch.cat([x for x in out_last["cls"]]).clone()
-        got_reg = torch.cat([x for x in out_last["reg"]]).clone()
+        got_cls, got_reg = out_last["cls"].cat.clone(), out_last["reg"].cat.clone()
         sync_all()
         if rank == 0:
             full = synth.collate([synth.make_scene(i, PRESET) for i in range(B)])
@@ -433,10 +432,10 @@ def run_forward(args):
     data_packed = L.pack_batch(synth.collate(scenes))   # one host blob per sample, made once (the dataset's job)
 
     def run_e2e(n, batch):
-        gather = (lambda o: shard.gather_outputs(o, plan)) if world > 1 else None
+        gather = (lambda o: shard.gather_outputs(o, plan, lazy=True)) if world > 1 else None
         mode = True if rank == 0 else "defer"
         res = None
-        for out in L.prefetch_forward(net, (batch for _ in range(n)), to_host=mode, post=gather):
+        for out in L.prefetch_forward(net, (batch for _ in range(n)), to_host=mode, post=gather, lazy_lists=True):
             res = out
         return res
 
@@ -462,7 +461,7 @@ def run_forward(args):
         t0 = time.perf_counter()
         o = step_device(net.stage(data_packed)) if world > 1 else net(data_packed)
         if rank == 0:
-            torch.cat(list(o["cls"])).cpu(), torch.cat(list(o["reg"])).cpu()
+            L._cat_of(o["cls"]).cpu(), L._cat_of(o["reg"]).cpu()
         torch.cuda.synchronize()
         lat.append(1e3 * (time.perf_counter() - t0))
         sync_all()

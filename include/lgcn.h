@@ -103,6 +103,24 @@ int lgcn_csr_build(const int64_t* const* h_u, const int64_t* const* h_v, const i
 int lgcn_scatter_csr_build(const int64_t* dst, const int64_t* src, int64_t n_edges, int64_t n_dst, int64_t n_src,
                            int32_t* rowptr, int32_t* col, void* workspace, int32_t* err_flag, void* stream);
 
+/* ------------------------------------------------------------------ graph construction before the path
+ * Scale-0 pre (is_suc = 0) / suc (is_suc = 1) node edges from the lane topology, in the reference's order
+ * (data.py:272-295): per lane the in-lane chain, then one boundary link per lane pair.  lane_idcs int64[n_nodes]
+ * (node -> lane, ascending, lanes 0..n_lanes-1), pairs int64[n_pairs,2] (lane, neighbour lane) SORTED by lane
+ * (data.py:302-317 appends them lane by lane; *err_flag is set otherwise).  u, v: int64[n_nodes - n_lanes + n_pairs].   */
+int64_t lgcn_scale0_workspace_bytes(int64_t n_lanes);
+int lgcn_scale0_edges(const int64_t* lane_idcs, int64_t n_nodes, int64_t n_lanes, const int64_t* pairs, int64_t n_pairs,
+                      int is_suc, int64_t* u, int64_t* v, void* workspace, int32_t* err_flag, void* stream);
+/* Left / right node edges of preprocess() (preprocess_data.py:287-392, cross_angle = None): for every node the nearest
+ * node among the lanes reachable as side neighbour or a predecessor / successor of it (side_pairs = left_pairs or
+ * right_pairs; lane-level int64[.,2]), kept if closer than cross_dist and heading within pi/4.  u (ascending), v:
+ * int64[>= n_nodes]; *h_count (host) receives the edge count — SYNCHRONISES (dataset-build-time code).               */
+int64_t lgcn_side_edges_workspace_bytes(int64_t n_nodes, int64_t n_lanes);
+int lgcn_side_edges(const float* ctrs, const float* feats, const int64_t* lane_idcs, int64_t n_nodes, int64_t n_lanes,
+                    const int64_t* side_pairs, int64_t n_side, const int64_t* pre_pairs, int64_t n_pre,
+                    const int64_t* suc_pairs, int64_t n_suc, float cross_dist, int64_t* u, int64_t* v, void* workspace,
+                    int64_t* h_count, void* stream);
+
 /* ------------------------------------------------------------------ multi-scale dilation (data.py:520-534)
  * Boolean CSR squaring with scipy's column order (reverse first discovery), bit-exact.  int32 CSR on the device.
  *   lgcn_dilate_csr0   : scale-0 edge list (int64 u = row, v = col; duplicates merged, columns ascending) -> CSR;

@@ -36,6 +36,10 @@ _SIGS = {
     "lgcn_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_csr_build": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_scatter_csr_build": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lgcn_scale0_workspace_bytes": (_i64, [_i64]),
+    "lgcn_scale0_edges": (_i32, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lgcn_side_edges_workspace_bytes": (_i64, [_i64, _i64]),
+    "lgcn_side_edges": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_dilate_workspace_bytes": (_i64, [_i64, _i64]),
     "lgcn_dilate_csr0": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "lgcn_dilate_bound": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -289,8 +289,12 @@ class Net(nn.Module):
         with torch.cuda.device(dev):
             graph = graph_gather(data["graph"])
             roi = subgraph_gather(data["subgraphs"], dev)
-            feat = self.input(roi)
-            feat = self.roi_net1(feat, roi)
-            feat = self.interactor(graph, roi, feat)
-            feat = self.roi_net2(feat, roi)
-            return {"roi_feat": feat, "graph": graph, "graphRoI": roi}
+            return {"roi_feat": self.forward_graphs(graph, roi), "graph": graph, "graphRoI": roi}
+
+    @torch.no_grad()
+    def forward_graphs(self, graph: Dict, roi: Dict) -> Tensor:
+        """The graph layers on already batched (device-resident) graphs: lanercnn.py:97-112."""
+        feat = self.input(roi)
+        feat = self.roi_net1(feat, roi)
+        feat = self.interactor(graph, roi, feat)
+        return self.roi_net2(feat, roi)

@@ -54,7 +54,8 @@ def make_plan(local_sizes: Sequence[int], group=None) -> GatherPlan:
     return GatherPlan(per_rank)
 
 
-def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, group=None) -> Dict[str, List[torch.Tensor]]:
+def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, group=None,
+                   lazy: bool = False) -> Dict[str, List[torch.Tensor]]:
     """All ranks receive every scene's ``cls``/``reg`` in global scene order with ONE collective: cls [A,K] and
     reg [A,K,T,2] are packed side by side into a [max_actors, K + K*T*2] buffer (1,464 B per actor in the
     reference config) and all_gathered; no host synchronisation when ``plan`` is given."""
@@ -79,7 +80,7 @@ def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, 
         buf[:n, k:] = reg.reshape(n, -1)
     full = torch.empty(world * plan.max_actors, width, dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(full, buf, group=group)
-    # compact the ranks' valid rows (2 small copies) and hand out per-scene lists whose views are created on first use
+    # compact the ranks' valid rows (2 small copies); with lazy=True the per-scene views are created on first use
     # (splitting a 128-scene result into 256 views costs ~0.4 ms of host time per step)
     from .lanegcn import scene_list
 
@@ -92,4 +93,4 @@ def gather_outputs(out: Dict[str, List[torch.Tensor]], plan: GatherPlan = None, 
     cls = valid[:, :k].contiguous()
     reg = valid[:, k:].contiguous().view((-1,) + tail)
     off = torch.zeros(1, dtype=torch.int32)
-    return {"cls": scene_list(cls, sizes, off, lazy=True), "reg": scene_list(reg, sizes, off, lazy=True)}
+    return {"cls": scene_list(cls, sizes, off, lazy=lazy), "reg": scene_list(reg, sizes, off, lazy=lazy)}

@@ -230,3 +230,63 @@ def seeded_state_dict(shapes: dict, seed: int = 0):
             w = 0.1 * rng.standard_normal(shape)
         out[name] = torch.from_numpy(w.astype(np.float32))
     return out
+
+
+def make_lane_rois(scene: dict, suc_hops: int = 2, pre_hops: int = 1, near: float = 5.0):
+    """Synthetic per-agent lane-RoI sub-graphs in the schema of the reference's ``generate_lane_roi``
+    (data_lrcnn.py:690-844: keys a2m{u,v}, node_mask, num_nodes, feats [n,8], agent_feat [80], agent_vel, pre/suc[6]{u,v},
+    left/right{u,v}; edges = the scene's node edges restricted to the RoI, re-indexed, in row-major (u, v) order).
+    The lane selection is a plain breadth-first walk (``suc_hops`` successors, ``pre_hops`` predecessors of the lane
+    nearest to the agent, plus their left / right neighbours) instead of the reference's velocity-dependent DFS: the
+    generator only has to produce realistically sized RoIs (~50-110 nodes) for the LaneRCNN benchmark (BASELINE
+    config 5) and for tests."""
+    g = scene["graph"]
+    lane_idcs = np.asarray(g["lane_idcs"], np.int64)
+    n_lanes = int(lane_idcs[-1]) + 1
+    adj = {k: [[] for _ in range(n_lanes)] for k in ("pre", "suc", "left", "right")}
+    for k in adj:
+        for i, j in np.asarray(g[k + "_pairs"], np.int64).reshape(-1, 2):
+            adj[k][i].append(int(j))
+    nodes_of = [np.nonzero(lane_idcs == i)[0] for i in range(n_lanes)]
+    subs = []
+    for a in range(len(scene["ctrs"])):
+        d = np.sqrt(((g["ctrs"] - scene["ctrs"][a]) ** 2).sum(1))
+        lanes = [int(lane_idcs[int(d.argmin())])]
+        for key, hops in (("suc", suc_hops), ("pre", pre_hops)):
+            frontier = [lanes[0]]
+            for _ in range(hops):
+                frontier = [j for i in frontier for j in adj[key][i]]
+                lanes += [j for j in frontier if j not in lanes]
+        for i in list(lanes):
+            lanes += [j for j in adj["left"][i] + adj["right"][i] if j not in lanes]
+        node_mask = np.concatenate([nodes_of[i] for i in lanes])
+        if len(node_mask) < 6:
+            continue
+        local = np.full(len(lane_idcs), -1, np.int64)
+        local[node_mask] = np.arange(len(node_mask))
+
+        def restrict(e):
+            u, v = local[np.asarray(e["u"], np.int64)], local[np.asarray(e["v"], np.int64)]
+            keep = (u >= 0) & (v >= 0)
+            u, v = u[keep], v[keep]
+            order = np.lexsort((v, u))       # np.nonzero of the dense relation matrix: row-major
+            return {"u": u[order], "v": v[order]}
+
+        sg = {"node_mask": node_mask, "num_nodes": len(node_mask)}
+        feats = np.zeros((len(node_mask), 8), np.float32)
+        feats[:, :2], feats[:, 2:4], feats[:, 4:6] = g["ctrs"][node_mask], g["feats"][node_mask], g["turn"][node_mask]
+        feats[:, 6], feats[:, 7] = g["control"][node_mask], g["intersect"][node_mask]
+        sg["feats"] = feats
+        traj = np.cumsum(scene["feats"][a, :, :2], 0) + scene["ctrs"][a] - np.sum(scene["feats"][a, :, :2], 0)
+        sg["agent_feat"] = np.concatenate([traj, scene["feats"][a, :, :2]], -1).reshape(-1).astype(np.float32)
+        sg["agent_vel"] = float(np.linalg.norm(scene["feats"][a, -1, :2]) * 10.0 + 0.1)
+        vs = np.nonzero(d[node_mask] < near)[0].astype(np.int32)
+        sg["a2m"] = {"u": np.zeros(len(vs), np.int32), "v": vs}
+        for k1 in ("pre", "suc"):
+            sg[k1] = [restrict(e) for e in g[k1]]
+        for k1 in ("left", "right"):
+            sg[k1] = restrict(g[k1])
+        if len(sg["pre"][0]["u"]) == 0 and len(sg["suc"][0]["u"]) == 0:
+            continue
+        subs.append(sg)
+    return subs

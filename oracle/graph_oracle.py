@@ -104,3 +104,69 @@ def pair_list(agt_ctrs, ctx_ctrs, dist_th, fix_empty_scene_offsets=False):
     if not hi:
         return np.zeros(0, np.int64), np.zeros(0, np.int64)
     return np.concatenate(hi), np.concatenate(wi)
+
+
+# --------------------------------------------------------------------------- data.py:272-295
+def scale0_edges(lane_idcs, pre_pairs, suc_pairs):
+    """Scale-0 pre / suc node edges from the lane topology, in the reference's order (data.py:272-295): per lane the
+    in-lane chain, then one boundary link per (lane, neighbour) pair; the pairs are the lane-level ``pre_pairs`` /
+    ``suc_pairs`` of the same function (data.py:302-317), which list a lane's neighbours in the same order."""
+    lane_idcs = np.asarray(lane_idcs, np.int64)
+    n_lanes = int(lane_idcs[-1]) + 1 if len(lane_idcs) else 0
+    node_idcs = [np.nonzero(lane_idcs == i)[0] for i in range(n_lanes)]
+    pre = {"u": [], "v": []}
+    suc = {"u": [], "v": []}
+    for i in range(n_lanes):
+        idcs = node_idcs[i]
+        pre["u"] += list(idcs[1:])
+        pre["v"] += list(idcs[:-1])
+        for a, j in np.asarray(pre_pairs, np.int64).reshape(-1, 2):
+            if a == i:
+                pre["u"].append(idcs[0])
+                pre["v"].append(node_idcs[j][-1])
+        suc["u"] += list(idcs[:-1])
+        suc["v"] += list(idcs[1:])
+        for a, j in np.asarray(suc_pairs, np.int64).reshape(-1, 2):
+            if a == i:
+                suc["u"].append(idcs[-1])
+                suc["v"].append(node_idcs[j][0])
+    as64 = lambda d: {k: np.asarray(v, np.int64) for k, v in d.items()}  # noqa: E731
+    return as64(pre), as64(suc)
+
+
+# --------------------------------------------------------------------------- preprocess_data.py:287-392
+def side_edges(ctrs, feats, lane_idcs, side_pairs, pre_pairs, suc_pairs, cross_dist):
+    """Left (or right) node edges of ``preprocess()`` with cross_angle=None: dense fp32 distance matrix, candidates =
+    nodes of the lanes reachable as side neighbour or a predecessor / successor of it, row minimum (first index on
+    ties), distance and heading filters.  numpy fp32 restatement of the torch ops, same order."""
+    ctrs, feats = np.asarray(ctrs, np.float32), np.asarray(feats, np.float32)
+    lane_idcs = np.asarray(lane_idcs, np.int64)
+    side_pairs = np.asarray(side_pairs, np.int64).reshape(-1, 2)
+    if len(side_pairs) == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    n_lanes = int(lane_idcs[-1]) + 1
+    d = ctrs[:, None, :] - ctrs[None, :, :]
+    dist = np.sqrt((d * d).sum(2, dtype=np.float32))
+    mk = lambda pairs: _dense(pairs, n_lanes)  # noqa: E731
+    mat = mk(side_pairs)
+    mat = (mat @ mk(pre_pairs) + mat @ mk(suc_pairs) + mat) > 0.5
+    masked = np.where(mat[lane_idcs[:, None], lane_idcs[None, :]], dist, np.float32(1e6))
+    vi = masked.argmin(1)
+    ok = masked[np.arange(len(ctrs)), vi] < np.float32(cross_dist)
+    ui = np.nonzero(ok)[0]
+    vi = vi[ok]
+    t1 = np.arctan2(feats[ui, 1], feats[ui, 0])
+    t2 = np.arctan2(feats[vi, 1], feats[vi, 0])
+    dt = np.abs(t1 - t2)
+    m = dt > np.float32(np.pi)
+    dt[m] = np.abs(dt[m] - np.float32(2 * np.pi))
+    m = dt < np.float32(0.25 * np.pi)
+    return ui[m].astype(np.int64), vi[m].astype(np.int64)
+
+
+def _dense(pairs, n):
+    m = np.zeros((n, n), np.float32)
+    pairs = np.asarray(pairs, np.int64).reshape(-1, 2)
+    if len(pairs):
+        m[pairs[:, 0], pairs[:, 1]] = 1
+    return m

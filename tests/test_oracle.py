@@ -137,3 +137,32 @@ def test_oracle_is_bit_identical_to_reference():
     for k in ("cls", "reg"):
         for a, b in zip(got[k], want[k]):
             assert torch.equal(a, b)
+
+
+def test_side_edges_oracle_matches_reference_golden():
+    """numpy restatement of preprocess() (preprocess_data.py:287-392) vs the reference's own output (goldens written by
+    tests/golden/make_golden_preprocess.py); scenes with hard=1 exercise the distance and heading filters."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_preprocess import SCENES, scene_graph
+
+    fx = golden("preprocess_lr")
+    for k, (preset, seed, hard) in enumerate(SCENES):
+        g = scene_graph(preset, seed, hard)
+        for side in ("left", "right"):
+            u, v = graph_oracle.side_edges(g["ctrs"], g["feats"], g["lane_idcs"], g[side + "_pairs"], g["pre_pairs"],
+                                           g["suc_pairs"], 6)
+            assert np.array_equal(u, fx[f"{k}_{side}_u"].astype(np.int64)), (preset, seed, side)
+            assert np.array_equal(v, fx[f"{k}_{side}_v"].astype(np.int64)), (preset, seed, side)
+        if hard:
+            assert 0 < len(fx[f"{k}_left_u"]) < g["num_nodes"] // 2, "hard scenes must lose edges to the filters"
+
+
+def test_scale0_edges_oracle_matches_generator():
+    """Restatement of data.py:272-295 vs the scale-0 lists the synthetic generator builds lane by lane."""
+    for preset, seed in (("tiny", 2), ("small", 9), ("argo-1.5k", 1)):
+        g = synth.make_scene(seed, preset)["graph"]
+        pre, suc = graph_oracle.scale0_edges(g["lane_idcs"], g["pre_pairs"], g["suc_pairs"])
+        for k in ("u", "v"):
+            assert np.array_equal(pre[k], g["pre"][0][k].astype(np.int64))
+            assert np.array_equal(suc[k], g["suc"][0][k].astype(np.int64))
