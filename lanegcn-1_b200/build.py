@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "liblgcn_b200.so")
 
-SOURCES = ["api.cu", "host_pack.cu", "graph.cu", "dilate.cu", "laneconv.cu", "att.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_wide.cu", "laneconv_fused.cu", "forward.cu", "actor_net.cu", "pred_net.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "host_pack.cu", "graph.cu", "dilate.cu", "laneconv.cu", "att.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_wide.cu", "laneconv_fused.cu", "laneconv_v2.cu", "forward.cu", "actor_net.cu", "pred_net.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HAVE_TC = int(os.path.exists(os.path.join(CSRC, "gemm_tc.cu")))

@@ -448,6 +448,22 @@ int make_map_2d(CUtensorMap* map, const float* base, int64_t cols, int64_t rows,
   LGCN_CHECK_ARG(r == CUDA_SUCCESS, "linear128(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
+// 2-D fp32 map with a 64-byte-wide box (16 floats) and SWIZZLE_64B: rows packed at 64 B, 16-byte chunk index XOR
+// ((row >> 1) & 3)
+int make_map_2d_sw64(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t ld, int box_rows) {
+  EncodeTiledFn encode = get_encode();
+  LGCN_CHECK_ARG(encode != nullptr, "linear128(tcgen05): cuTensorMapEncodeTiled not available from the driver");
+  LGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "linear128(tcgen05): tensor must be 16-byte aligned");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LGCN_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (64 B box) failed (%d)", (int)r);
+  return 0;
+}
 int make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
   EncodeTiledFn encode = get_encode();
   LGCN_CHECK_ARG(encode != nullptr, "linear128(tcgen05): cuTensorMapEncodeTiled not available from the driver");

@@ -43,6 +43,10 @@
 
 using namespace tc;
 
+int lgcn_launch_laneconv_v2(const float* x, const float* xa, const int32_t* tab, float* out, int64_t n_nodes,
+                            const int32_t* n_dev, int n_keys, const float* w_hi, const float* w_lo, const float* gn,
+                            cudaStream_t st);
+
 namespace {
 
 #ifndef LGCN_FUSED_WAIT
@@ -202,6 +206,12 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
 #else
 #define LGCN_TL_MMA(c) (void)0
 #define LGCN_TL_PROD(c) (void)0
+#endif
+#ifdef LGCN_TIMELINE2   // fine-grained producer stamps (warp 4, lane 0): 16 x 32-bit clocks per stage into a.tl viewed as int32 [1024][16]
+  uint32_t tk[16];
+#define LGCN_TK(i) asm volatile("mov.u32 %0, %%clock;" : "=r"(tk[i]) :: "memory")
+#else
+#define LGCN_TK(i) (void)0
 #endif
   const int flush_keys = (dbg & 64) ? (1 << 20) : (dbg & 512) ? 5 : kFlushKeys;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
@@ -398,6 +408,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       const float* base = !linear ? X : kk == 0 ? src0 : kk == 1 ? src1 : src2;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        if (dbg & 1024) break;   // ablation: no cp.async instructions at all
         const int v = vr[i];
         const int row = 8 * i + (lane >> 2);
         const float* p = v >= 0 ? base + (int64_t)v * LGCN_C : XA + (int64_t)(v < -1 ? -2 - v : 0) * LGCN_C;
@@ -410,11 +421,13 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     };
     auto take = [&](float4(&cur)[4], int slot) {   // this lane's row: 64 B of the slot (stage s; s+1, s+2 may be pending)
       asm volatile("cp.async.wait_group 2;" ::: "memory");
+      LGCN_TK(2);
       __syncwarp();
       const uint32_t src = xblk + slot * 16384 + lane * 64;
 #pragma unroll
       for (int c = 0; c < 4; ++c) cur[c] = ld_shared_f4(src + ((c ^ ((lane >> 1) & 3)) << 4));
       __syncwarp();   // every lane has read: the slot may be refilled
+      LGCN_TK(3);
     };
     uint32_t a_phase = 0, acc_uses = 0;
     int as = 0;
@@ -480,9 +493,11 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     };
     auto stage_end = [&]() {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      LGCN_TK(7);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * as);
+      LGCN_TK(8);
       if (++as == kAStages) {
         as = 0;
         a_phase ^= 1;
@@ -700,18 +715,22 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           }
           float4 cur[4];
           LGCN_TL_PROD(3);
+          LGCN_TK(0);
           stage_peek();
+          LGCN_TK(1);
           take(cur, xs);
           LGCN_TL_PROD(4);
           stage_begin_peeked();
+          LGCN_TK(4);
           LGCN_TL_PROD(5);
           if (!(dbg & 32)) put16(cur, h * 16);
+          LGCN_TK(5);
           // refill the slot with stage + 3 (chunk kc-1 of the next key) while the tcgen05.st complete; at kc == 0 the
           // sources of the next key come first, and that longer sequence runs after the publish instead
           if (kc != 0) issue(vrn, kc - 1, xs, kk + 1);
+          LGCN_TK(6);
           stage_end();
           LGCN_TL_PROD(6);
-          ++tls;
           if (kc == 0) {
             // all groups but the two newest have landed: the entry of key kk+1 (requested a key ago) is readable
             sources((int)t, kk + 1, (kseq + 1) & 3, vrn);
@@ -725,7 +744,18 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           // more pipelining than the shared fixed costs save.  Two producer TEAMS -- warps 4-7 / 8-11 producing the
           // stages of one parity each, whole 32-float chunks, 5 arrivals per stage -- was slower too, 560 us, and so
           // was its barrier skeleton: the per-warp instruction stream is not what bounds the feed.)
+          LGCN_TK(9);
           if (kc == 2 && flush_here) flush_main();
+          LGCN_TK(10);
+#ifdef LGCN_TIMELINE2
+          if (a.tl && (dbg & 256) && blockIdx.x == 0 && e == 0 && lane == 0 && tls < 1024) {
+            uint32_t* t2 = reinterpret_cast<uint32_t*>(a.tl) + tls * 16;
+#pragma unroll
+            for (int i = 0; i < 11; ++i) t2[i] = tk[i];
+            t2[11] = (uint32_t)(kk * 4 + kc);
+          }
+#endif
+          ++tls;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) vr[i] = vrn[i];
@@ -909,6 +939,7 @@ extern "C" int lgcn_debug_timeline(long long* device_buffer) {
   g_timeline = device_buffer;
   return 0;
 }
+long long* lgcn_timeline_buffer() { return g_timeline; }
 
 // ------------------------------------------------------------------ linear mode: lgcn_linear128 on this kernel
 namespace {
@@ -1092,6 +1123,9 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
     k_multi_sum<<<num_sms() * 4, 256, 0, st>>>(x, v.hdr, v.mdesc, v.mcol, xa, v.max_multi);
     LGCN_LAUNCH_OK();
   }
+  // the chain form runs on the second-generation kernel (laneconv_v2.cu); debug flag 2048 keeps this one
+  if (chain && !LGCN_BF16_CROSS && !(lgcn_debug_get() & 2048))
+    return lgcn_launch_laneconv_v2(x, xa, v.tab, out, n_nodes, n_dev, n_keys, w_hi, w_lo, gn, st);
   const int nkw = n_keys + 1 + (chain ? 1 : 0);
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, out, LGCN_C, n_nodes, LGCN_C)) return rc;

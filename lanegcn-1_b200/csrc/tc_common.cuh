@@ -215,12 +215,14 @@ EncodeTiledFn get_encode();
 int make_out_map(CUtensorMap* map, float* out, int64_t cols, int64_t rows, int64_t ldo);
 // generic 2-D fp32 map: [rows, cols] with row stride ld floats, box {box_cols, box_rows}, SWIZZLE_128B
 int make_map_2d(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows);
+// 2-D fp32 map with a 16-float (64 B) x box_rows box, SWIZZLE_64B
+int make_map_2d_sw64(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t ld, int box_rows);
 // the same over a bf16 tensor (cols / ld / box_cols in bf16 elements)
 int make_map_2d_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows);
 // Per-DEVICE cached state (one process may drive several GPUs: the Python layer keys its workspaces per device and
 // wraps calls in torch.cuda.device(dev)).  num_sms(): SM count of the CURRENT device.  first_use(family): true
 // exactly once per (current device, kernel family) — cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device.
-enum { kFamLinearTc = 0, kFamWideTc = 1, kFamFused = 2, kFamCount = 4 };
+enum { kFamLinearTc = 0, kFamWideTc = 1, kFamFused = 2, kFamFusedV2 = 3, kFamCount = 4 };
 constexpr int kMaxDevices = 64;
 int current_device();
 int num_sms();
