@@ -25,13 +25,18 @@ int lgcn_debug_flags(int flags);
 /* Profiling aid: device buffer [1024][8] of int64 clock stamps filled by CTA 0 of the aggregate-first LaneConv kernel
  * while debug flag 256 is set (tools/timeline_fused.py). */
 int lgcn_debug_timeline(long long* device_buffer);
-/* Per-kernel timing for the benchmark: while enabled, lgcn_laneconv_stack / lgcn_att_forward bracket their
- * launches with CUDA events on the launching stream.  lgcn_prof_collect SYNCHRONISES on those events, returns
- * summed milliseconds and launch counts per kind (0 wide projection GEMM, 1 LaneConv gather, 2 ctr2 linear,
- * 3 whole Att layer, 4 aggregate-first LaneConv block incl. its multi-source pre-pass; ARRAYS OF 8, the rest
- * reserved) and resets.  lgcn_prof_enable returns the previous state. */
+/* Per-kernel timing for the benchmark: while enabled, the library brackets its LaneConv / Att launches with CUDA
+ * events on the launching stream.  on = 1: eager launches only (stream captures are left alone); on = 2: launches
+ * INSIDE a stream capture only, as external event-record nodes (cudaEventRecordExternal) of the captured graph, so
+ * every replay re-records them and the kernels are timed in the product's own sequence (branch overlap, priorities).
+ * lgcn_prof_collect SYNCHRONISES on those events, returns summed milliseconds and launch counts per kind (0 wide
+ * projection GEMM, 1 LaneConv gather, 2 ctr2 linear, 3 whole Att layer, 4 aggregate-first LaneConv block incl. its
+ * multi-source pre-pass, 5 the block's main kernel alone (k_laneconv_v2); ARRAYS OF 8, the rest reserved) and forgets
+ * the events; lgcn_prof_peek does the same without forgetting them (read after each replay of a mode-2 graph).
+ * lgcn_prof_enable returns the previous state. */
 int lgcn_prof_enable(int on);
 int lgcn_prof_collect(double* h_ms_by_kind, int64_t* h_launches_by_kind);
+int lgcn_prof_peek(double* h_ms_by_kind, int64_t* h_launches_by_kind);
 
 #ifdef __cplusplus
 }

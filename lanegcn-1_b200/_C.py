@@ -29,6 +29,7 @@ _SIGS = {
     "lgcn_launch_count": (_i64, []),
     "lgcn_prof_enable": (_i32, [_i32]),
     "lgcn_prof_collect": (_i32, [_vp, _vp]),
+    "lgcn_prof_peek": (_i32, [_vp, _vp]),
     "lgcn_pack_host": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32]),
     "lgcn_stage_scenes": (_i32, [_vp, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),
     "lgcn_offset_indices": (_i32, [_vp, _i32, _vp, _vp, _i32, _i64, _vp, _vp]),

@@ -8,9 +8,10 @@
 // contiguous bytes).  Arithmetic is plain fp32 FMA (the reference's convs are true fp32: cudnn.allow_tf32 = False):
 // 8.6 MFLOP per actor, compute-bound on the FP32 pipe; GroupNorm(1) normalises over all (C, L) of an actor, two-pass.
 //
-// Thread mapping of a conv (a [rows = actors x L_out] x [K = taps x C_in] x [C_out] product): a lane owns 4 output
-// channels (distinct, coalesced weight reads) x RT consecutive steps of one actor (input rows are warp-broadcast
-// 128-bit shared loads): 4 x RT x 4 FMAs per 4 + RT shared loads.
+// Thread mapping of a conv (a [rows = actors x L_out] x [K = taps x C_in] x [C_out] product): a lane owns CPL output
+// channels (4, 2 or 1: distinct, coalesced weight reads; chosen per layer so that no thread is left without outputs) x RT
+// consecutive steps of one actor (input rows are warp-broadcast 128-bit shared loads): CPL x RT x 4 FMAs per 4 + RT
+// shared loads.
 #include <atomic>
 
 #include "common.cuh"
@@ -62,18 +63,19 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 
 // Raw convolution: in [G][LIN + 2][CIN] -> out rows 1..LOUT of [G][LOUT + 2][COUT]   (LIN = LOUT * STRIDE; K = 3: pad 1,
 // K = 1: pad 0).  All threads of the CTA call it; ends with a __syncthreads().
-template <int CIN, int COUT, int K, int STRIDE, int LOUT, int RT>
+template <int CIN, int COUT, int K, int STRIDE, int LOUT, int RT, int CPL = 4>
 __device__ __forceinline__ void conv(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ Wt,
                                      float* __restrict__ wst) {
   constexpr int LIN = LOUT * STRIDE;
-  constexpr int LPG = COUT / 4;              // lanes per row group
+  constexpr int LPG = COUT / CPL;            // lanes per row group (a lane owns CPL output channels)
   constexpr int GROUPS = kThreads / LPG;     // row groups in the CTA
   constexpr int TILES_PER_ACTOR = LOUT / RT;
   constexpr int N_TILES = kActors * TILES_PER_ACTOR;
   constexpr int NR = K == 3 ? (RT - 1) * STRIDE + 3 : RT;   // input rows a tile touches
   constexpr int CH = CIN < kWChunk ? CIN : kWChunk;
-  static_assert(LOUT % RT == 0 && COUT % 4 == 0 && CIN % 4 == 0 && CIN % CH == 0, "shape");
-  const int co0 = (threadIdx.x % LPG) * 4;
+  static_assert(LOUT % RT == 0 && COUT % CPL == 0 && kThreads % LPG == 0 && CIN % 4 == 0 && CIN % CH == 0, "shape");
+  static_assert(CPL == 1 || CPL == 2 || CPL == 4, "channels per lane");
+  const int co0 = (threadIdx.x % LPG) * CPL;
   const int group = threadIdx.x / LPG;
 
   for (int tile0 = 0; tile0 < N_TILES; tile0 += GROUPS) {
@@ -82,9 +84,11 @@ __device__ __forceinline__ void conv(const float* __restrict__ in, float* __rest
     const int g = live ? tile / TILES_PER_ACTOR : 0, l0 = live ? (tile % TILES_PER_ACTOR) * RT : 0;
     // first input row (padded coordinates) of the tile: K = 3 -> l0 * S + kk, K = 1 -> l0 * S + 1
     const float* xin = in + ((int64_t)g * (LIN + 2) + l0 * STRIDE + (K == 3 ? 0 : 1)) * CIN;
-    float acc[RT][4];
+    float acc[RT][CPL];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc[r][c] = 0.f;
     // weight chunks stream through a two-stage cp.async ring: chunk c+1 is in flight while chunk c is consumed
     auto prefetch = [&](int c0, int stage) {   // wst[stage][kk][ci][co] <- Wt[kk][c0 + ci][co]
       float* dst = wst + stage * (3 * kWChunk * 128);
@@ -112,14 +116,25 @@ __device__ __forceinline__ void conv(const float* __restrict__ in, float* __rest
 #pragma unroll
           for (int kk = 0; kk < K; ++kk) {
             const float* wp = wcur + ((int64_t)kk * CH + ci) * COUT + co0;
-            const float4 w0 = lds4(wp), w1 = lds4(wp + COUT), w2 = lds4(wp + 2 * COUT), w3 = lds4(wp + 3 * COUT);
+            float w[4][CPL];   // [input channel ci + q][this lane's output channel]
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if constexpr (CPL == 4) {
+                const float4 t = lds4(wp + q * COUT);
+                w[q][0] = t.x; w[q][1] = t.y; w[q][2] = t.z; w[q][3] = t.w;
+              } else if constexpr (CPL == 2) {
+                const float2 t = *reinterpret_cast<const float2*>(wp + q * COUT);
+                w[q][0] = t.x; w[q][1] = t.y;
+              } else {
+                w[q][0] = wp[q * COUT];
+              }
+            }
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
               const float4 v = x[K == 3 ? r * STRIDE + kk : r];
-              acc[r][0] = fmaf(v.w, w3.x, fmaf(v.z, w2.x, fmaf(v.y, w1.x, fmaf(v.x, w0.x, acc[r][0]))));
-              acc[r][1] = fmaf(v.w, w3.y, fmaf(v.z, w2.y, fmaf(v.y, w1.y, fmaf(v.x, w0.y, acc[r][1]))));
-              acc[r][2] = fmaf(v.w, w3.z, fmaf(v.z, w2.z, fmaf(v.y, w1.z, fmaf(v.x, w0.z, acc[r][2]))));
-              acc[r][3] = fmaf(v.w, w3.w, fmaf(v.z, w2.w, fmaf(v.y, w1.w, fmaf(v.x, w0.w, acc[r][3]))));
+#pragma unroll
+              for (int c = 0; c < CPL; ++c)
+                acc[r][c] = fmaf(v.w, w[3][c], fmaf(v.z, w[2][c], fmaf(v.y, w[1][c], fmaf(v.x, w[0][c], acc[r][c]))));
             }
           }
         }
@@ -129,8 +144,14 @@ __device__ __forceinline__ void conv(const float* __restrict__ in, float* __rest
     if (live) {
       float* o = out + ((int64_t)g * (LOUT + 2) + l0 + 1) * COUT + co0;
 #pragma unroll
-      for (int r = 0; r < RT; ++r)
-        *reinterpret_cast<float4*>(o + (int64_t)r * COUT) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      for (int r = 0; r < RT; ++r) {
+        if constexpr (CPL == 4)
+          *reinterpret_cast<float4*>(o + (int64_t)r * COUT) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        else if constexpr (CPL == 2)
+          *reinterpret_cast<float2*>(o + (int64_t)r * COUT) = make_float2(acc[r][0], acc[r][1]);
+        else
+          o[(int64_t)r * COUT] = acc[r][0];
+      }
     }
   }
   __syncthreads();
@@ -241,17 +262,17 @@ constexpr int kSmemFloats = kOffStat + 2 * kActors + 8;
 constexpr int kSmemBytes = kSmemFloats * 4;
 
 // Res1d (layers.py:142-190): x -> relu(GN(conv2(relu(GN(conv1(x))))) + shortcut); h, y: scratch; result in `dst`
-template <int CIN, int COUT, int STRIDE, int LOUT, int RT, int I1, int I2, int ID>
+template <int CIN, int COUT, int STRIDE, int LOUT, int RT, int I1, int I2, int ID, int CPL = 4>
 __device__ __forceinline__ void res1d(const float* x, float* h, float* y, float* d, float* dst, const float* pack, float* wst,
                                       float* stats) {
   const ConvW c1 = layer<I1>(pack), c2 = layer<I2>(pack);
-  conv<CIN, COUT, 3, STRIDE, LOUT, RT>(x, h, c1.w, wst);
+  conv<CIN, COUT, 3, STRIDE, LOUT, RT, CPL>(x, h, c1.w, wst);
   gn_apply<COUT, LOUT>(h, h, c1.gamma, c1.beta, nullptr, GN_RELU, stats);
-  conv<COUT, COUT, 3, 1, LOUT, RT>(h, y, c2.w, wst);
+  conv<COUT, COUT, 3, 1, LOUT, RT, CPL>(h, y, c2.w, wst);
   if constexpr (ID >= 0) {
     const ConvW cd = layer<ID>(pack);
     gn_apply<COUT, LOUT>(y, y, c2.gamma, c2.beta, nullptr, 0, stats);
-    conv<CIN, COUT, 1, STRIDE, LOUT, RT>(x, d, cd.w, wst);
+    conv<CIN, COUT, 1, STRIDE, LOUT, RT, CPL>(x, d, cd.w, wst);
     gn_apply<COUT, LOUT>(d, d, cd.gamma, cd.beta, nullptr, 0, stats);
     add_relu<COUT, LOUT>(y, d);   // the blocks with a shortcut conv leave their result in y (dst == y)
   } else {
@@ -280,19 +301,22 @@ k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __res
     reinterpret_cast<float4*>(X0)[i] = v;
   }
   __syncthreads();
+  // Channels per lane (last template argument) are chosen so that every thread of the CTA owns outputs in every layer:
+  // kActors x L x C outputs / kThreads = 10 per thread in groups 0-2 (4 channels per lane would leave 75 / 50 / 50 % of
+  // the threads without a tile there)
   // groups.0 (L = 20, 32 channels)
-  res1d<4, 32, 1, 20, 10, 0, 1, 2>(X0, P, Q, R, Q, pack, wst, stats);      // -> Q
-  res1d<32, 32, 1, 20, 10, 3, 4, -1>(Q, P, R, nullptr, F0, pack, wst, stats);   // -> F0
+  res1d<4, 32, 1, 20, 10, 0, 1, 2, 1>(X0, P, Q, R, Q, pack, wst, stats);      // -> Q
+  res1d<32, 32, 1, 20, 10, 3, 4, -1, 1>(Q, P, R, nullptr, F0, pack, wst, stats);   // -> F0
   // groups.1 (L = 10, 64 channels)
-  res1d<32, 64, 2, 10, 5, 5, 6, 7>(F0, P, Q, R, Q, pack, wst, stats);
-  res1d<64, 64, 1, 10, 5, 8, 9, -1>(Q, P, R, nullptr, F1, pack, wst, stats);
+  res1d<32, 64, 2, 10, 5, 5, 6, 7, 2>(F0, P, Q, R, Q, pack, wst, stats);
+  res1d<64, 64, 1, 10, 5, 8, 9, -1, 2>(Q, P, R, nullptr, F1, pack, wst, stats);
   // groups.2 (L = 5, 128 channels)
-  res1d<64, 128, 2, 5, 5, 10, 11, 12>(F1, P, Q, R, Q, pack, wst, stats);
-  res1d<128, 128, 1, 5, 5, 13, 14, -1>(Q, P, R, nullptr, F2, pack, wst, stats);
+  res1d<64, 128, 2, 5, 5, 10, 11, 12, 2>(F1, P, Q, R, Q, pack, wst, stats);
+  res1d<128, 128, 1, 5, 5, 13, 14, -1, 2>(Q, P, R, nullptr, F2, pack, wst, stats);
   // FPN: out = lateral2(f2); out = up(out) + lateral1(f1); out = up(out) + lateral0(f0)            lanegcn.py:256-261
   {
     const ConvW l2 = layer<17>(pack), l1 = layer<16>(pack), l0 = layer<15>(pack);
-    conv<128, 128, 3, 1, 5, 5>(F2, P, l2.w, wst);
+    conv<128, 128, 3, 1, 5, 5, 2>(F2, P, l2.w, wst);
     gn_apply<128, 5>(P, P, l2.gamma, l2.beta, nullptr, 0, stats);
     upsample2<128, 5>(P, Q);
     conv<64, 128, 3, 1, 10, 5>(F1, R, l1.w, wst);

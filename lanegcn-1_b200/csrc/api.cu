@@ -14,15 +14,21 @@ static std::atomic<long long> g_launches{0};
 void lgcn_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" int64_t lgcn_launch_count(void) { return g_launches.load(); }
 
-// ---- per-kernel timing: event pairs on the launching stream, summed per kind by lgcn_prof_collect
+// ---- per-kernel timing: event pairs on the launching stream, summed per kind by lgcn_prof_collect / lgcn_prof_peek.
+// Mode 1 brackets EAGER launches (captures are left alone); mode 2 brackets launches INSIDE a stream capture with
+// external event-record nodes, so every replay of that graph re-records them: the kernels are timed in the very
+// sequence (branch overlap, stream priorities) the product runs.
 struct ProfEv { cudaEvent_t a, b; int kind; };
 static std::vector<ProfEv> g_prof_pool;
 static size_t g_prof_used = 0;
-static bool g_prof_on = false;
-LgcnProfScope::LgcnProfScope(int kind, cudaStream_t s) : slot(-1), st(s) {
+static int g_prof_on = 0;
+LgcnProfScope::LgcnProfScope(int kind, cudaStream_t s) : slot(-1), st(s), external(false) {
   if (!g_prof_on) return;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;  // timing is for eager runs
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) return;
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (capturing != (g_prof_on == 2)) return;
+  external = capturing;
   if (g_prof_used == g_prof_pool.size()) {
     ProfEv e;
     if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
@@ -30,17 +36,17 @@ LgcnProfScope::LgcnProfScope(int kind, cudaStream_t s) : slot(-1), st(s) {
   }
   slot = (int)g_prof_used++;
   g_prof_pool[slot].kind = kind;
-  cudaEventRecord(g_prof_pool[slot].a, st);
+  cudaEventRecordWithFlags(g_prof_pool[slot].a, st, external ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 LgcnProfScope::~LgcnProfScope() {
-  if (slot >= 0) cudaEventRecord(g_prof_pool[slot].b, st);
+  if (slot >= 0) cudaEventRecordWithFlags(g_prof_pool[slot].b, st, external ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 extern "C" int lgcn_prof_enable(int on) {
   const int prev = g_prof_on;
-  g_prof_on = on != 0;
+  g_prof_on = on < 0 || on > 2 ? 0 : on;
   return prev;
 }
-extern "C" int lgcn_prof_collect(double* ms_by_kind, int64_t* launches_by_kind) {
+static int prof_sum(double* ms_by_kind, int64_t* launches_by_kind) {
   for (int k = 0; k < LGCN_PROF_KINDS; ++k) {
     ms_by_kind[k] = 0.0;
     launches_by_kind[k] = 0;
@@ -52,8 +58,13 @@ extern "C" int lgcn_prof_collect(double* ms_by_kind, int64_t* launches_by_kind) 
     ms_by_kind[g_prof_pool[i].kind] += ms;
     launches_by_kind[g_prof_pool[i].kind] += 1;
   }
-  g_prof_used = 0;
   return 0;
+}
+extern "C" int lgcn_prof_peek(double* ms_by_kind, int64_t* launches_by_kind) { return prof_sum(ms_by_kind, launches_by_kind); }
+extern "C" int lgcn_prof_collect(double* ms_by_kind, int64_t* launches_by_kind) {
+  const int rc = prof_sum(ms_by_kind, launches_by_kind);
+  g_prof_used = 0;
+  return rc;
 }
 static int g_engine = -1;  // -1: not decided yet
 static int g_debug = 0;

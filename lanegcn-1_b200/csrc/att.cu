@@ -10,7 +10,7 @@ __device__ __forceinline__ bool within(float ax, float ay, float cx, float cy, f
   return d <= th;
 }
 
-#define PAIR_WARPS 8
+#define PAIR_WARPS 16   // kIndexThreads / 32
 
 // FILL == false: cnt[r] = number of context rows of r's scene within th.
 // FILL == true : write the pairs of row r at row_start[r].., hi = local row + hi_off[b], wi = j + wi_off[b]; entries at
@@ -39,26 +39,79 @@ k_pairs(const float2* __restrict__ agt_ctrs, const float2* __restrict__ ctx_ctrs
     h = (int32_t)r - agt_off[b] + hi_off[b];
     w0 = wi_off[b] - c0;
   }
-  for (int32_t j0 = c0; j0 < c1; j0 += 32) {
-    const int32_t j = j0 + lane;
-    bool p = false;
-    if (j < c1) {
-      const float2 c = ctx_ctrs[j];
-      p = within(a.x, a.y, c.x, c.y, th);
+  // four 32-wide chunks of context centres per iteration: the loads are independent, so a row with ~1.5 k context
+  // rows (M2A) pays ~12 dependent memory round trips instead of ~48
+  for (int32_t j0 = c0; j0 < c1; j0 += 128) {
+    float2 c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int32_t j = j0 + 32 * q + lane;
+      c[q] = j < c1 ? ctx_ctrs[j] : make_float2(0.f, 0.f);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, p);
-    if (FILL && p) {
-      const int32_t o = pos + run + __popc(m & ((1u << lane) - 1u));
-      if (o < p_cap) {
-        if (hi32) hi32[o] = h;
-        if (wi32) wi32[o] = j + w0;
-        if (hi64) hi64[o] = h;
-        if (wi64) wi64[o] = j + w0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int32_t j = j0 + 32 * q + lane;
+      const bool p = j < c1 && within(a.x, a.y, c[q].x, c[q].y, th);
+      const unsigned m = __ballot_sync(0xffffffffu, p);
+      if (FILL && p) {
+        const int32_t o = pos + run + __popc(m & ((1u << lane) - 1u));
+        if (o < p_cap) {
+          if (hi32) hi32[o] = h;
+          if (wi32) wi32[o] = j + w0;
+          if (hi64) hi64[o] = h;
+          if (wi64) wi64[o] = j + w0;
+        }
       }
+      run += __popc(m);
     }
-    run += __popc(m);
   }
   if (!FILL && lane == 0) cnt[r] = run;
+}
+
+// Same contract, ONE THREAD per agent row: for lists whose scenes have few context rows (A2M: ~1.5 k lane nodes x 20
+// actors per scene, 193 k agent rows per batch) a warp per row leaves most lanes idle and pays a dozen dependent
+// loads per warp; here a warp covers 32 consecutive rows (nearly always of one scene, so the scene lookup and the
+// context centres are warp-uniform, broadcast loads) and a thread writes its row's few pairs itself, in context order.
+template <bool FILL>
+__global__ void __launch_bounds__(kIndexThreads)
+k_pairs_thin(const float2* __restrict__ agt_ctrs, const float2* __restrict__ ctx_ctrs,
+             const int32_t* __restrict__ agt_off, const int32_t* __restrict__ ctx_off, int n_scenes,
+             int64_t n_agt_cap, const int32_t* __restrict__ n_agt_dev, float th, int32_t* __restrict__ cnt,
+             const int32_t* __restrict__ row_start, const int32_t* __restrict__ hi_off, const int32_t* __restrict__ wi_off,
+             int32_t* __restrict__ hi32, int32_t* __restrict__ wi32, int64_t* __restrict__ hi64, int64_t* __restrict__ wi64,
+             int64_t p_cap) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= lgcn_devn(n_agt_dev, n_agt_cap)) return;
+  int32_t pos = 0;
+  if (FILL) {
+    pos = row_start[r];
+    if (row_start[r + 1] == pos) return;  // nothing to write for this row
+  }
+  const int b = scene_of(agt_off, n_scenes, (int32_t)r);
+  const int32_t c0 = ctx_off[b], c1 = ctx_off[b + 1];
+  const float2 a = agt_ctrs[r];
+  int32_t h = 0, w0 = 0;
+  if (FILL) {
+    h = (int32_t)r - agt_off[b] + hi_off[b];
+    w0 = wi_off[b] - c0;
+  }
+  int32_t run = 0;
+  for (int32_t j = c0; j < c1; ++j) {
+    const float2 c = __ldg(ctx_ctrs + j);
+    if (within(a.x, a.y, c.x, c.y, th)) {
+      if (FILL) {
+        const int32_t o = pos + run;
+        if (o < p_cap) {
+          if (hi32) hi32[o] = h;
+          if (wi32) wi32[o] = j + w0;
+          if (hi64) hi64[o] = h;
+          if (wi64) wi64[o] = j + w0;
+        }
+      }
+      ++run;
+    }
+  }
+  if (!FILL) cnt[r] = run;
 }
 
 // Per-scene totals from the scanned counts, then the reference's offset bookkeeping (lanegcn.py:681-687: a scene
@@ -170,18 +223,25 @@ extern "C" int64_t lgcn_pairs_workspace_bytes(int64_t n_agt, int n_scenes) {
 int lgcn_launch_pairs(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off, const int32_t* ctx_off,
                       int n_scenes, int64_t n_agt_cap, const int32_t* n_agt_dev, float th, int keep_quirk,
                       int32_t* rowptr, void* workspace, int64_t p_cap, int32_t* hi32, int32_t* wi32, int32_t* p_total,
-                      int32_t* status, int32_t* p_exact, int overflow_bit, int empty_bit, cudaStream_t st) {
+                      int32_t* status, int32_t* p_exact, int overflow_bit, int empty_bit, int64_t n_ctx_hint, cudaStream_t st) {
   LGCN_CHECK_ARG(n_scenes >= 1 && n_agt_cap >= 0, "pairs: n_scenes %d n_agt %lld", n_scenes, (long long)n_agt_cap);
   LGCN_CHECK_ARG(n_agt_cap < (int64_t)1 << 31, "pairs: n_agt exceeds int32");
   int32_t* row_start = (int32_t*)workspace;
   int32_t* hi_off = row_start + lgcn_align_up(n_agt_cap + 1, 64);
   int32_t* wi_off = hi_off + lgcn_align_up(n_scenes, 64);
   int32_t* cnt = wi_off + lgcn_align_up(n_scenes, 64);
-  const unsigned grid = lgcn_cdiv(n_agt_cap, PAIR_WARPS);
+  // scenes with few context rows (n_ctx_hint = their total or its capacity; 0 = unknown): one thread per agent row
+  const bool thin = n_ctx_hint > 0 && n_ctx_hint <= (int64_t)48 * n_scenes;
+  const unsigned grid = thin ? lgcn_cdiv(n_agt_cap, kIndexThreads) : lgcn_cdiv(n_agt_cap, PAIR_WARPS);
   if (n_agt_cap > 0) {
-    k_pairs<false><<<grid, PAIR_WARPS * 32, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off,
-                                                     n_scenes, n_agt_cap, n_agt_dev, th, cnt, nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr, nullptr, nullptr, 0);
+    if (thin)
+      k_pairs_thin<false><<<grid, kIndexThreads, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes,
+                                                n_agt_cap, n_agt_dev, th, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                nullptr, nullptr, 0);
+    else
+      k_pairs<false><<<grid, PAIR_WARPS * 32, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off,
+                                                       n_scenes, n_agt_cap, n_agt_dev, th, cnt, nullptr, nullptr, nullptr,
+                                                       nullptr, nullptr, nullptr, nullptr, 0);
     LGCN_LAUNCH_OK();
   }
   int32_t* scratch = cnt + lgcn_align_up(n_agt_cap, 64);  // [0..1024] scan scratch, [1056] used_rows
@@ -194,9 +254,14 @@ int lgcn_launch_pairs(const float* agt_ctrs, const float* ctx_ctrs, const int32_
                                                                    p_total, status, p_exact, overflow_bit, empty_bit);
   LGCN_LAUNCH_OK();
   if (p_cap >= 0 && n_agt_cap > 0 && (hi32 || wi32)) {
-    k_pairs<true><<<grid, PAIR_WARPS * 32, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off,
-                                                    n_scenes, n_agt_cap, n_agt_dev, th, nullptr, row_start, hi_off, wi_off,
-                                                    hi32, wi32, nullptr, nullptr, p_cap);
+    if (thin)
+      k_pairs_thin<true><<<grid, kIndexThreads, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off, n_scenes,
+                                               n_agt_cap, n_agt_dev, th, nullptr, row_start, hi_off, wi_off, hi32, wi32,
+                                               nullptr, nullptr, p_cap);
+    else
+      k_pairs<true><<<grid, PAIR_WARPS * 32, 0, st>>>((const float2*)agt_ctrs, (const float2*)ctx_ctrs, agt_off, ctx_off,
+                                                      n_scenes, n_agt_cap, n_agt_dev, th, nullptr, row_start, hi_off, wi_off,
+                                                      hi32, wi32, nullptr, nullptr, p_cap);
     LGCN_LAUNCH_OK();
   }
   return 0;
@@ -207,7 +272,7 @@ extern "C" int lgcn_pairs_count(const float* agt_ctrs, const float* ctx_ctrs, co
                                 int32_t* rowptr, void* workspace, int64_t* h_total, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = lgcn_launch_pairs(agt_ctrs, ctx_ctrs, agt_off, ctx_off, n_scenes, n_agt, nullptr, th, keep_quirk, rowptr,
-                                 workspace, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, st))
+                                 workspace, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, st))
     return rc;
   if (h_total) {
     int32_t p = 0;

@@ -37,13 +37,20 @@ void lgcn_count_launch();
   } while (0)
 
 // optional per-kernel timing (lgcn_prof_*): CUDA events recorded on the launching stream around a launch
-enum { LGCN_PROF_WIDE = 0, LGCN_PROF_GATHER = 1, LGCN_PROF_CTR2 = 2, LGCN_PROF_ATT = 3, LGCN_PROF_FUSED = 4, LGCN_PROF_KINDS = 8 };
+enum { LGCN_PROF_WIDE = 0, LGCN_PROF_GATHER = 1, LGCN_PROF_CTR2 = 2, LGCN_PROF_ATT = 3, LGCN_PROF_FUSED = 4, LGCN_PROF_BLOCK_KERNEL = 5, LGCN_PROF_KINDS = 8 };
 struct LgcnProfScope {
   int slot;
   cudaStream_t st;
+  bool external;
   LgcnProfScope(int kind, cudaStream_t st);
   ~LgcnProfScope();
 };
+
+// CTA size of the index kernels that run next to ActorNet at the head of the forward (graph build, pair lists).  Two
+// ActorNet CTAs hold 224 of an SM's 228 KB of shared memory, and every CTA reserves 1 KB of it: only TWO more CTAs fit
+// beside them whatever their own footprint, so the threads have to come from the CTA size (128-thread CTAs ran 256
+// threads per SM: k_csr_finish 186 us).
+constexpr int kIndexThreads = 512;
 
 static inline int64_t lgcn_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned lgcn_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -164,7 +171,7 @@ int lgcn_launch_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys
 int lgcn_launch_pairs(const float* agt_ctrs, const float* ctx_ctrs, const int32_t* agt_off, const int32_t* ctx_off,
                       int n_scenes, int64_t n_agt_cap, const int32_t* n_agt_dev, float th, int keep_quirk,
                       int32_t* rowptr, void* workspace, int64_t p_cap, int32_t* hi32, int32_t* wi32, int32_t* p_total,
-                      int32_t* status, int32_t* p_exact, int overflow_bit, int empty_bit, cudaStream_t st);
+                      int32_t* status, int32_t* p_exact, int overflow_bit, int empty_bit, int64_t n_ctx_hint, cudaStream_t st);
 int lgcn_launch_mlp2_in(const float* p, const int32_t* ip, const float* q, const int32_t* iq, const float* W1,
                         const float* b1, float* h, int64_t m_cap, const int32_t* m_dev, cudaStream_t st);
 int lgcn_launch_segsum_gn_relu(const float* a, const float* c, const int32_t* rowptr, const float* gamma,

@@ -224,11 +224,12 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
     const int32_t* ctx_o[3] = {a.actor_off, a.node_off, a.actor_off};
     const int64_t n_agt[3] = {N, A, A};
     const int32_t* n_agt_dev[3] = {n_nodes, n_actors, n_actors};
+    const int64_t n_ctx[3] = {A, N, A};
     for (int i = 0; i < 3; ++i)
       if (int rc = lgcn_launch_pairs(agt_c[i], ctx_c[i], agt_o[i], ctx_o[i], a.cap_scenes, n_agt[i], n_agt_dev[i],
                                      a.dist_th[i], a.keep_pair_quirk, (int32_t*)(ws + L.p_rowptr[i]), ws + L.p_ws[i],
                                      a.cap_pairs[i], (int32_t*)(ws + L.p_hi[i]), (int32_t*)(ws + L.p_wi[i]), p_tot + i,
-                                     a.status, a.status + 1 + i, LGCN_ST_OVERFLOW_A2M << i, LGCN_ST_EMPTY_A2M << i, st))
+                                     a.status, a.status + 1 + i, LGCN_ST_OVERFLOW_A2M << i, LGCN_ST_EMPTY_A2M << i, n_ctx[i], st))
         return rc;
   }
 

@@ -6,10 +6,12 @@
 // ------------------------------------------------------------------ index widening + scene offsets
 template <typename T>
 __global__ void k_offset_indices(const T* __restrict__ local, const int64_t* __restrict__ seg_start,
-                                 const int64_t* __restrict__ seg_add, int64_t* __restrict__ out) {
-  const int s = blockIdx.x;
+                                 const int64_t* __restrict__ seg_add, int n_segments, int64_t* __restrict__ out) {
+  // one warp per segment; CTAs of 16 warps (see kIndexThreads in common.cuh)
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_segments) return;
   const int64_t beg = seg_start[s], end = seg_start[s + 1], add = seg_add[s];
-  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) out[i] = (int64_t)local[i] + add;
+  for (int64_t i = beg + (threadIdx.x & 31); i < end; i += 32) out[i] = (int64_t)local[i] + add;
 }
 
 extern "C" int lgcn_offset_indices(const void* local, int idx_bytes, const int64_t* seg_start,
@@ -20,11 +22,11 @@ extern "C" int lgcn_offset_indices(const void* local, int idx_bytes, const int64
   if (n_segments == 0 || total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (idx_bytes == 2)
-    k_offset_indices<int16_t><<<n_segments, 128, 0, st>>>((const int16_t*)local, seg_start, seg_add, out);
+    k_offset_indices<int16_t><<<lgcn_cdiv(n_segments, kIndexThreads / 32), kIndexThreads, 0, st>>>((const int16_t*)local, seg_start, seg_add, n_segments, out);
   else if (idx_bytes == 4)
-    k_offset_indices<int32_t><<<n_segments, 128, 0, st>>>((const int32_t*)local, seg_start, seg_add, out);
+    k_offset_indices<int32_t><<<lgcn_cdiv(n_segments, kIndexThreads / 32), kIndexThreads, 0, st>>>((const int32_t*)local, seg_start, seg_add, n_segments, out);
   else
-    k_offset_indices<int64_t><<<n_segments, 128, 0, st>>>((const int64_t*)local, seg_start, seg_add, out);
+    k_offset_indices<int64_t><<<lgcn_cdiv(n_segments, kIndexThreads / 32), kIndexThreads, 0, st>>>((const int64_t*)local, seg_start, seg_add, n_segments, out);
   LGCN_LAUNCH_OK();
   return 0;
 }
@@ -209,9 +211,11 @@ struct EdgeSets {
 };
 
 __device__ __forceinline__ int key_of(const EdgeSets& es, int64_t e) {
+  // boundaries are ascending: the key is the number of boundaries at or below e (independent loads, no search chain)
+  const int n_keys = es.n_keys;
   int k = 0;
-#pragma unroll 1
-  while (k + 1 < es.n_keys && e >= es.start[k + 1]) ++k;
+#pragma unroll
+  for (int q = 1; q < LGCN_MAX_KEYS; ++q) k += (q < n_keys && e >= es.start[q]) ? 1 : 0;
   return k;
 }
 
@@ -262,33 +266,30 @@ __global__ void k_csr_place(const EdgeSets es_val, const EdgeSets* __restrict__ 
   }
 }
 
-// One thread per destination row: order the row's edge ids ascending (== key order, then edge-list order:
-// the stable-by-destination order CPU index_add_ accumulates in) and emit col = v*(K+1) + (k+1).
-// Rows are short (about a dozen entries on lane graphs), so an in-place insertion sort is the right tool;
-// the atomics above only decide a scratch order that this pass erases, so the CSR is deterministic.
+// One thread per CSR SLOT: the slot's edge id e gives its row (u) and source (v); its final position inside the row is
+// the number of edge ids of that row below e (ids are distinct), i.e. rows come out ordered by edge id == key order,
+// then edge-list order: the stable-by-destination order CPU index_add_ accumulates in.  col = v*(K+1) + (k+1).
+// The atomics above only decide the scratch order that this pass erases, so the CSR is deterministic.
+// (The first version walked a row per thread with an insertion sort: rows with a merge upstream carry up to ~26 entries,
+// nearly every warp had one, and the kernel took 124 us stand-alone — 200+ beside ActorNet — for 2.4 M edges.)
 template <bool DEV>
-__global__ void k_csr_finish(const EdgeSets es_val, const EdgeSets* __restrict__ es_dev, int64_t n_cap,
-                             const int32_t* __restrict__ n_dev, int plain, const int32_t* __restrict__ rowptr,
-                             int32_t* __restrict__ slot_edge, int32_t* __restrict__ col) {
+__global__ void __launch_bounds__(kIndexThreads)
+k_csr_finish(const EdgeSets es_val, const EdgeSets* __restrict__ es_dev, int64_t n_cap,
+             const int32_t* __restrict__ n_dev, int plain, const int32_t* __restrict__ rowptr,
+             const int32_t* __restrict__ slot_edge, int32_t* __restrict__ col) {
   const EdgeSets& es = DEV ? *es_dev : es_val;
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= lgcn_devn(n_dev, n_cap)) return;
-  const int32_t beg = rowptr[r], end = rowptr[r + 1];
-  for (int32_t i = beg + 1; i < end; ++i) {
-    const int32_t x = slot_edge[i];
-    int32_t j = i - 1;
-    while (j >= beg && slot_edge[j] > x) {
-      slot_edge[j + 1] = slot_edge[j];
-      --j;
-    }
-    slot_edge[j + 1] = x;
-  }
-  const int32_t nb = es.n_keys + 1;
-  for (int32_t i = beg; i < end; ++i) {
+  const int32_t n_slots = rowptr[lgcn_devn(n_dev, n_cap)];
+  const int n_keys = es.n_keys;
+  const int32_t nb = n_keys + 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = slot_edge[i];
     const int k = key_of(es, e);
-    const int64_t v = es.v[k][e - es.start[k]];
-    col[i] = plain ? (int32_t)v : (int32_t)(v * nb + (k + 1));
+    const int64_t off = e - es.start[k];
+    const int64_t u = es.u[k][off], v = es.v[k][off];
+    const int32_t beg = rowptr[u], end = rowptr[u + 1];
+    int32_t rank = 0;
+    for (int32_t j = beg; j < end; ++j) rank += slot_edge[j] < (int32_t)e ? 1 : 0;
+    col[beg + rank] = plain ? (int32_t)v : (int32_t)(v * nb + (k + 1));
   }
 }
 
@@ -305,17 +306,17 @@ static int csr_launch(const EdgeSets& es, const EdgeSets* es_dev, int64_t E_cap,
   int32_t* slot_edge = (int32_t*)((char*)workspace + lgcn_align_up(4 * n_cap, 256));
   int32_t* scan_scratch = (int32_t*)((char*)slot_edge + lgcn_align_up(4 * E_cap, 256));
   if (lgcn_zero_async(cnt, 4 * n_cap, st) || lgcn_zero_async(err_flag, 4, st)) return -2;
-  const unsigned eb = E_cap ? min(lgcn_cdiv(E_cap, 256), 148u * 16u) : 0u;
+  const unsigned eb = E_cap ? min(lgcn_cdiv(E_cap, kIndexThreads), 148u * 8u) : 0u;
   if (eb) {
-    k_csr_hist<DEV><<<eb, 256, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, cnt, err_flag);
+    k_csr_hist<DEV><<<eb, kIndexThreads, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, cnt, err_flag);
     LGCN_LAUNCH_OK();
   }
   if (lgcn_launch_exclusive_scan(cnt, rowptr, n_cap, n_dev, scan_scratch, st)) return -2;
   if (eb) {
     if (lgcn_zero_async(cnt, 4 * n_cap, st)) return -2;
-    k_csr_place<DEV><<<eb, 256, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, rowptr, cnt, slot_edge);
+    k_csr_place<DEV><<<eb, kIndexThreads, 0, st>>>(es, es_dev, n_cap, n_dev, n_src, rowptr, cnt, slot_edge);
     LGCN_LAUNCH_OK();
-    k_csr_finish<DEV><<<lgcn_cdiv(n_cap, 128), 128, 0, st>>>(es, es_dev, n_cap, n_dev, plain, rowptr, slot_edge, col);
+    k_csr_finish<DEV><<<eb, kIndexThreads, 0, st>>>(es, es_dev, n_cap, n_dev, plain, rowptr, slot_edge, col);
     LGCN_LAUNCH_OK();
   }
   return 0;

@@ -816,38 +816,105 @@ struct PlanHdr {
   int32_t n_multi, n_mcol, pad[62];
 };
 
-__global__ void k_plan_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_keys,
-                             int64_t n_cap, const int32_t* __restrict__ n_dev, int32_t* __restrict__ hdr,
-                             int32_t* __restrict__ tab, int2* __restrict__ mdesc, int32_t* __restrict__ mcol,
-                             int64_t max_multi) {
+// One thread per destination row, two passes over the row's CSR entries (sorted by key; col = v * nb + k + 1):
+//   1. every key's run -> the table entry of the single-source keys, and the row's number of multi-source keys / of their
+//      sources;  a block-wide scan turns those into offsets, ONE pair of atomics per CTA reserves the CTA's descriptors
+//      (the first version paid two same-address atomics per multi-source key — 160 k at batch 128 — and walked the
+//      row through a data-dependent while loop: 70 us stand-alone);
+//   2. rows that have multi-source keys write their descriptors, source lists and table entries.
+// The descriptor order depends on which CTA reserves first; what a table entry points at does not.
+constexpr int kPlanThreads = 512;
+__global__ void __launch_bounds__(kPlanThreads)
+k_plan_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_keys,
+             int64_t n_cap, const int32_t* __restrict__ n_dev, int32_t* __restrict__ hdr,
+             int32_t* __restrict__ tab, int2* __restrict__ mdesc, int32_t* __restrict__ mcol,
+             int64_t max_multi) {
+  __shared__ int32_t wsum[2][kPlanThreads / 32];
+  __shared__ int32_t base[2];
   const int64_t n_nodes = lgcn_devn(n_dev, n_cap);
   const int64_t n_rows_padded = (n_nodes + kTileM - 1) / kTileM * kTileM;
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_rows_padded) return;
+  const bool in_range = m < n_rows_padded;
   int32_t* my = tab + ((m >> 7) * n_keys << 7) + (m & 127);
-  const int nb = n_keys + 1;
-  int32_t e = 0, end = 0;
+  const uint32_t nb = n_keys + 1;
+  const uint64_t magic = ((1ull << 40) + nb - 1) / nb;   // c / nb == (c * magic) >> 40 for c < 2^31, nb <= 17
+  int32_t beg = 0, end = 0;
   if (m < n_nodes) {
-    e = rowptr[m];
+    beg = rowptr[m];
     end = rowptr[m + 1];
   }
-  for (int k = 0; k < n_keys; ++k) {   // entries of a row are sorted by key (col = v * nb + k + 1)
-    int32_t val = -1;
-    const int32_t e0 = e;
-    while (e < end && col[e] % nb == k + 1) ++e;
-    const int32_t cnt = e - e0;
-    if (cnt == 1) {
-      val = col[e0] / nb;
-    } else if (cnt > 1) {
-      const int32_t i = atomicAdd(hdr, 1);
-      if (i < max_multi) {
-        const int32_t s = atomicAdd(hdr + 1, cnt);
-        mdesc[i] = make_int2(s, cnt);
-        for (int32_t j = 0; j < cnt; ++j) mcol[s + j] = col[e0 + j] / nb;
-        val = -2 - i;
+  int32_t n_multi = 0, n_src = 0;
+  if (in_range) {
+    for (int k = 0; k < n_keys; ++k) my[(int64_t)k << 7] = -1;
+    uint32_t run_key = 0, run_first = 0;
+    int32_t run_len = 0;
+    auto close_run = [&]() {
+      if (run_len == 1) my[(int64_t)(run_key - 1) << 7] = (int32_t)run_first;
+      else if (run_len > 1) { ++n_multi; n_src += run_len; }
+    };
+#pragma unroll 4
+    for (int32_t j = beg; j < end; ++j) {
+      const uint32_t c = (uint32_t)col[j];
+      const uint32_t src = (uint32_t)((c * magic) >> 40), key = c - src * nb;
+      if (key != run_key) {
+        close_run();
+        run_key = key; run_first = src; run_len = 0;
       }
+      ++run_len;
     }
-    my[(int64_t)k << 7] = val;
+    close_run();
+  }
+  // block-wide exclusive scan of (n_multi, n_src)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t inc[2] = {n_multi, n_src};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, inc[q], o);
+      if (lane >= o) inc[q] += t;
+    }
+    if (lane == 31) wsum[q][warp] = inc[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      int32_t v = lane < kPlanThreads / 32 ? wsum[q][lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      if (lane < kPlanThreads / 32) wsum[q][lane] = v;                     // inclusive over warps
+      if (lane == kPlanThreads / 32 - 1) base[q] = v ? atomicAdd(hdr + q, v) : 0;   // hdr[0]: descriptors, hdr[1]: sources
+    }
+  }
+  __syncthreads();
+  if (!n_multi) return;
+  int32_t di = base[0] + (warp ? wsum[0][warp - 1] : 0) + inc[0] - n_multi;   // this row's first descriptor ...
+  int32_t si = base[1] + (warp ? wsum[1][warp - 1] : 0) + inc[1] - n_src;     // ... and first source slot
+  int32_t j = beg;
+  while (j < end) {
+    const uint32_t c = (uint32_t)col[j];
+    const uint32_t key = c - (uint32_t)((c * magic) >> 40) * nb;
+    int32_t j1 = j + 1;
+    while (j1 < end) {
+      const uint32_t c1 = (uint32_t)col[j1];
+      if (c1 - (uint32_t)((c1 * magic) >> 40) * nb != key) break;
+      ++j1;
+    }
+    const int32_t cnt = j1 - j;
+    if (cnt > 1) {
+      if (di < max_multi) {
+        mdesc[di] = make_int2(si, cnt);
+        for (int32_t q = 0; q < cnt; ++q) mcol[si + q] = (int32_t)(((uint32_t)col[j + q] * magic) >> 40);
+        my[(int64_t)(key - 1) << 7] = -2 - di;
+      }
+      ++di;
+      si += cnt;
+    }
+    j = j1;
   }
 }
 
@@ -921,7 +988,7 @@ int lgcn_launch_plan_build(const int32_t* rowptr, const int32_t* col, int n_keys
   if (int rc = lgcn_zero_async(v.hdr, 256, st)) return rc;
   const int64_t rows = (n_nodes + kTileM - 1) / kTileM * kTileM;
   if (rows == 0 || n_keys == 0) return 0;
-  k_plan_build<<<lgcn_cdiv(rows, 256), 256, 0, st>>>(rowptr, col, n_keys, n_nodes, n_dev, v.hdr, v.tab, v.mdesc, v.mcol,
+  k_plan_build<<<lgcn_cdiv(rows, kPlanThreads), kPlanThreads, 0, st>>>(rowptr, col, n_keys, n_nodes, n_dev, v.hdr, v.tab, v.mdesc, v.mcol,
                                                     v.max_multi);
   LGCN_LAUNCH_OK();
   return 0;
@@ -1124,8 +1191,10 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
     LGCN_LAUNCH_OK();
   }
   // the chain form runs on the second-generation kernel (laneconv_v2.cu); debug flag 2048 keeps this one
-  if (chain && !LGCN_BF16_CROSS && !(lgcn_debug_get() & 2048))
+  if (chain && !LGCN_BF16_CROSS && !(lgcn_debug_get() & 2048)) {
+    LgcnProfScope ps(LGCN_PROF_BLOCK_KERNEL, st);   // the dominant kernel on its own (bench.py's roofline)
     return lgcn_launch_laneconv_v2(x, xa, v.tab, out, n_nodes, n_dev, n_keys, w_hi, w_lo, gn, st);
+  }
   const int nkw = n_keys + 1 + (chain ? 1 : 0);
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, out, LGCN_C, n_nodes, LGCN_C)) return rc;
@@ -1137,6 +1206,7 @@ int lgcn_launch_laneconv_fused(const float* x, float* out, void* plan, int64_t n
   a.tl = g_timeline;
   const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
+  LgcnProfScope ps(LGCN_PROF_BLOCK_KERNEL, st);
   k_laneconv_fused<false><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
   LGCN_LAUNCH_OK();
   return 0;

@@ -270,12 +270,14 @@ k_laneconv_v2(const V2Args a, const __grid_constant__ CUtensorMap out_map, const
         kk = 0;
         t += grid;
       }
+      // row 4j + rsub of this warp's block is live iff 4j < rows_left; one base pointer per key, constant offsets per j
+      const int64_t m_first = (int64_t)t * kTileM + g * kRowsPerGW + rsub;
+      const int64_t rows_left = t < n_tiles ? M - m_first : 0;
+      const int32_t* p = tab + (((int64_t)t * n_keys + (kk - 1)) << 7) + g * kRowsPerGW + rsub;
 #pragma unroll
       for (int j = 0; j < kInstrPerGW; ++j) {
-        const int row = g * kRowsPerGW + 4 * j + rsub;
-        const int64_t m = (int64_t)t * kTileM + row;
         int s = -1;
-        if (t < n_tiles && m < M) s = kk == 0 ? (int)m : __ldg(tab + (((int64_t)t * n_keys + (kk - 1)) << 7) + row);
+        if (4 * j < rows_left) s = kk == 0 ? (int)m_first + 4 * j : __ldg(p + 4 * j);
         v[j] = s;
       }
     };
