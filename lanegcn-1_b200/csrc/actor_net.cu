@@ -19,7 +19,8 @@
 namespace {
 
 constexpr int kActors = 2;      // actors per CTA; 112 KB of shared memory per CTA -> two CTAs per SM, so one CTA's
-constexpr int kThreads = 128;   // barriers / GroupNorm passes overlap the other's FMA phases
+constexpr int kThreads = 256;   // barriers / GroupNorm passes overlap the other's FMA phases; 16 warps per SM (with 128
+                                // threads the schedulers held two warps each and issued 0.42 instructions per cycle)
 constexpr int kWChunk = 8;      // input channels per staged weight chunk (x 3 taps x 128 outputs x 4 B = 12 KB), two stages
 
 struct ConvW {
@@ -301,32 +302,32 @@ k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __res
     reinterpret_cast<float4*>(X0)[i] = v;
   }
   __syncthreads();
-  // Channels per lane (last template argument) are chosen so that every thread of the CTA owns outputs in every layer:
-  // kActors x L x C outputs / kThreads = 10 per thread in groups 0-2 (4 channels per lane would leave 75 / 50 / 50 % of
-  // the threads without a tile there)
+  // Rows per tile and channels per lane (the last two shape arguments) are chosen so that every thread of the CTA owns
+  // outputs in every layer: kActors x L x C outputs / kThreads = 5 per thread in groups 0-2 (10 rows x 4 channels would
+  // leave most threads without a tile there)
   // groups.0 (L = 20, 32 channels)
-  res1d<4, 32, 1, 20, 10, 0, 1, 2, 1>(X0, P, Q, R, Q, pack, wst, stats);      // -> Q
-  res1d<32, 32, 1, 20, 10, 3, 4, -1, 1>(Q, P, R, nullptr, F0, pack, wst, stats);   // -> F0
+  res1d<4, 32, 1, 20, 5, 0, 1, 2, 1>(X0, P, Q, R, Q, pack, wst, stats);      // -> Q
+  res1d<32, 32, 1, 20, 5, 3, 4, -1, 1>(Q, P, R, nullptr, F0, pack, wst, stats);   // -> F0
   // groups.1 (L = 10, 64 channels)
-  res1d<32, 64, 2, 10, 5, 5, 6, 7, 2>(F0, P, Q, R, Q, pack, wst, stats);
-  res1d<64, 64, 1, 10, 5, 8, 9, -1, 2>(Q, P, R, nullptr, F1, pack, wst, stats);
+  res1d<32, 64, 2, 10, 5, 5, 6, 7, 1>(F0, P, Q, R, Q, pack, wst, stats);
+  res1d<64, 64, 1, 10, 5, 8, 9, -1, 1>(Q, P, R, nullptr, F1, pack, wst, stats);
   // groups.2 (L = 5, 128 channels)
-  res1d<64, 128, 2, 5, 5, 10, 11, 12, 2>(F1, P, Q, R, Q, pack, wst, stats);
-  res1d<128, 128, 1, 5, 5, 13, 14, -1, 2>(Q, P, R, nullptr, F2, pack, wst, stats);
+  res1d<64, 128, 2, 5, 5, 10, 11, 12, 1>(F1, P, Q, R, Q, pack, wst, stats);
+  res1d<128, 128, 1, 5, 5, 13, 14, -1, 1>(Q, P, R, nullptr, F2, pack, wst, stats);
   // FPN: out = lateral2(f2); out = up(out) + lateral1(f1); out = up(out) + lateral0(f0)            lanegcn.py:256-261
   {
     const ConvW l2 = layer<17>(pack), l1 = layer<16>(pack), l0 = layer<15>(pack);
-    conv<128, 128, 3, 1, 5, 5, 2>(F2, P, l2.w, wst);
+    conv<128, 128, 3, 1, 5, 5, 1>(F2, P, l2.w, wst);
     gn_apply<128, 5>(P, P, l2.gamma, l2.beta, nullptr, 0, stats);
     upsample2<128, 5>(P, Q);
-    conv<64, 128, 3, 1, 10, 5>(F1, R, l1.w, wst);
+    conv<64, 128, 3, 1, 10, 5, 2>(F1, R, l1.w, wst);
     gn_apply<128, 10>(R, Q, l1.gamma, l1.beta, nullptr, GN_ACCUM, stats);
     upsample2<128, 10>(Q, P);
-    conv<32, 128, 3, 1, 20, 10>(F0, R, l0.w, wst);
+    conv<32, 128, 3, 1, 20, 10, 2>(F0, R, l0.w, wst);
     gn_apply<128, 20>(R, P, l0.gamma, l0.beta, nullptr, GN_ACCUM, stats);
   }
   // output Res1d, last step only                                                                  lanegcn.py:262
-  res1d<128, 128, 1, 20, 10, 18, 19, -1>(P, Q, R, nullptr, R, pack, wst, stats);
+  res1d<128, 128, 1, 20, 10, 18, 19, -1, 2>(P, Q, R, nullptr, R, pack, wst, stats);
   for (int i = threadIdx.x; i < kActors * 32; i += kThreads) {
     const int g = i >> 5, c = (i & 31) * 4;
     if (a0 + g < A)
