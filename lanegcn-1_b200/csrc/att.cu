@@ -305,6 +305,7 @@ k_mlp2_in(const float2* __restrict__ p, const int32_t* __restrict__ ip, const fl
           const int32_t* __restrict__ iq, const float* __restrict__ W1, const float* __restrict__ b1,
           float* __restrict__ h, int64_t m_cap, const int32_t* __restrict__ m_dev) {
   const int lane = threadIdx.x & 31;
+  lgcn_pdl_trigger();
   const int64_t m = lgcn_devn(m_dev, m_cap);
   // W1 is [128,2] row-major: this lane's 4 output channels are rows lane*4..lane*4+3 = 8 contiguous floats
   const float4 w01 = reinterpret_cast<const float4*>(W1)[lane * 2];

@@ -52,6 +52,32 @@ struct LgcnProfScope {
 // threads per SM: k_csr_finish 186 us).
 constexpr int kIndexThreads = 512;
 
+// Programmatic dependent launch (PDL).  A kernel launched through lgcn_launch_pdl may START while its predecessor on the
+// stream is still draining: its CTAs take SMs as they free up and run their prologue (barrier init, tensor-memory
+// allocation, norm vectors) up to lgcn_pdl_wait(), which returns once the predecessor has completed and flushed.
+// Rules: (1) such a kernel executes lgcn_pdl_wait() in EVERY thread before it reads or writes anything another kernel
+// of the stream touches (weights are static: fine before); (2) kernels that may precede one call lgcn_pdl_trigger()
+// first thing (without it the dependent simply starts when they end).  Both are no-ops in a normal launch.
+// Debug flag 16384 (include/lgcn_debug.h) turns the attribute off.
+__device__ __forceinline__ void lgcn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void lgcn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+int lgcn_debug_get();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lgcn_launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (lgcn_debug_get() & 16384) ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t lgcn_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned lgcn_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -24,6 +24,7 @@ k_gather_gn_relu(const float* __restrict__ base, int64_t base_ld, const float* _
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                  int64_t n_rows, const int32_t* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
+  lgcn_pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
   if (row >= lgcn_devn(n_dev, n_rows)) return;
   const int32_t beg = rowptr[row], end = rowptr[row + 1];

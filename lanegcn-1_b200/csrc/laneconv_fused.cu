@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                  const __grid_constant__ CUtensorMap whi_map, const __grid_constant__ CUtensorMap wlo_map) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  lgcn_pdl_trigger();
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   if (sbase & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,6 +179,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  lgcn_pdl_wait();   // everything above touched only this CTA's shared / tensor memory and the (static) norm vectors
 
   // scalars only below (a by-value struct captured by reference in a lambda ends up in local memory)
   const int64_t M = lgcn_devn(a.m_dev, a.M);
@@ -923,6 +925,7 @@ __global__ void __launch_bounds__(256)
 k_multi_sum(const float* __restrict__ X, const int32_t* __restrict__ hdr, const int2* __restrict__ mdesc,
             const int32_t* __restrict__ mcol, float* __restrict__ XA, int64_t max_multi) {
   const int lane = threadIdx.x & 31;
+  lgcn_pdl_trigger();
   int64_t n = hdr[0];
   if (n > max_multi) n = max_multi;
   for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
@@ -1164,8 +1167,8 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   a.flags = la.flags; a.M = la.m; a.m_dev = la.m_dev; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
   const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  if (la.ks == 4) k_laneconv_fused<true, true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
-  else k_laneconv_fused<true><<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  if (la.ks == 4) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
+  else LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   LGCN_LAUNCH_OK();
   if (slot >= 0) {
     std::lock_guard<std::mutex> lock(g_ring_mu);

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 k_laneconv_v2(const V2Args a, const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap whi_map,
               const __grid_constant__ CUtensorMap wlo_map) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  lgcn_pdl_trigger();
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   if (sbase & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +120,7 @@ k_laneconv_v2(const V2Args a, const __grid_constant__ CUtensorMap out_map, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  lgcn_pdl_wait();   // everything above touched only this CTA's shared / tensor memory and the (static) norm vectors
 
   const int64_t M = lgcn_devn(a.m_dev, a.M);
   const float* __restrict__ X = a.X;
@@ -630,7 +632,7 @@ int lgcn_launch_laneconv_v2(const float* x, const float* xa, const int32_t* tab,
   a.tl = (a.dbg & 256) ? reinterpret_cast<uint32_t*>(lgcn_timeline_buffer()) : nullptr;
   const int64_t n_tiles = (n_nodes + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  k_laneconv_v2<<<grid, kNumThreads, kSmemTotal, st>>>(a, map, mhi, mlo);
+  LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_v2, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   LGCN_LAUNCH_OK();
   return 0;
 }

@@ -12,6 +12,9 @@ dev = torch.device("cuda", 0)
 shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_shapes.json")))
 net = L.Net(L.config); net.load_state_dict(synth.seeded_state_dict(shapes, 0)); net = net.to(dev).eval()
 data = synth.collate(synth.make_scenes(B, "argo-1.5k"))
+if len(sys.argv) > 3:
+    from lanegcn_b200 import _C
+    _C.lib().lgcn_debug_flags(int(sys.argv[3]))
 staged = net.stage(data)
 for _ in range(5):
     net.forward_device(staged)
