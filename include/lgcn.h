@@ -318,6 +318,12 @@ typedef struct LgcnForwardArgs {
   int32_t* status;
   LgcnForwardWeights w;
   void* workspace;                            /* lgcn_forward_workspace_bytes(&args)                               */
+  void* aux_streams[2];                       /* optional (NULL = none): two more streams of the same device.  Kernels
+                                                 that do not depend on each other are forked onto them and joined back
+                                                 inside the call — the pair lists beside the CSR / plan build, the
+                                                 query and agt Linears of an Att layer beside its pair-side chain — so
+                                                 they become parallel branches of a captured graph.  The library keeps
+                                                 three fork / join events per device for this (created on first use). */
 } LgcnForwardArgs;
 
 /* ------------------------------------------------------------------ ActorNet (lanegcn.py:212-263) as ONE kernel

@@ -100,7 +100,7 @@ class ForwardArgs(C.Structure):
                 ("dims", _vp), ("node_off", _vp), ("actor_off", _vp), ("node_ctrs", _vp), ("node_feats", _vp),
                 ("turn", _vp), ("control", _vp), ("intersect", _vp), ("actor_ctrs", _vp), ("local_idx", _vp),
                 ("segs", _vp), ("nodes", _vp), ("actors", _vp), ("status", _vp), ("w", ForwardWeights),
-                ("workspace", _vp)]
+                ("workspace", _vp), ("aux_streams", _vp * 2)]
 
 
 STAGE_GRAPH, STAGE_MAPNET, STAGE_A2M, STAGE_M2M, STAGE_M2A, STAGE_A2A, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63

@@ -361,9 +361,11 @@ int lgcn_att_split_weights(const float* wpack, float* WH, float* WL, cudaStream_
 int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs, const float* ctx_ctrs,
                    const int32_t* hi, const int32_t* wi, const int32_t* rowptr, int64_t n_agt, const int32_t* n_agt_dev,
                    int64_t n_ctx, int64_t n_pairs, const int32_t* n_pairs_dev, const float* wpack, const float* WH,
-                   const float* WL, void* workspace, cudaStream_t st) {
+                   const float* WL, void* workspace, cudaStream_t st, const LgcnFork* fk) {
   if (n_agt <= 0) return 0;
   LgcnProfScope ps(LGCN_PROF_ATT, st);
+  static const LgcnFork serial = {{nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  if (!fk) fk = &serial;
   const AttW w = att_unpack(wpack);
   const int64_t pb = lgcn_align_up(n_pairs * LGCN_C * 4, 1024), ab = lgcn_align_up(n_agt * LGCN_C * 4, 1024);
   float* P0 = (float*)workspace;
@@ -393,23 +395,30 @@ int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, cons
   LGCN_CHECK_ARG(n_pairs > 0, "att_forward: no agent/context pair within the distance threshold in any scene "
                               "(the reference raises at lanegcn.py:688: torch.cat of an empty list)");
   LGCN_CHECK_ARG(ctx && agt_ctrs && ctx_ctrs && hi && wi && rowptr, "att_forward: NULL argument");
-  // dist = relu(GN(L(relu(L2(agt_ctrs[hi] - ctx_ctrs[wi])))))                      lanegcn.py:693-694
-  if (int rc = lgcn_launch_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, n_pairs_dev, st)) return rc;
-  LinearArgs d2 = with_w(pair_rows(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1), 0);
-  if (int rc = lgcn_launch_linear(d2, st)) return rc;
+  // Three independent chains start a layer: dist (pair rows), query, and the agent-side Linear `agt`; with auxiliary
+  // streams the last two run beside the first (the layer's critical path is then 6 kernels instead of 8).
+  if (fk->fork(0, st) || fk->fork(1, st)) return -2;
   // query = relu(GN(L(agts[hi])))  — a per-row function: computed per agent when that is fewer rows   :696
   // (decided on the capacities when the sizes live on the device)
   const float* q;
   const int32_t* qidx;
   if (n_agt <= n_pairs) {
     LinearArgs qa = with_w(agt_rows(agts_in, nullptr, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, A0), 1);
-    if (int rc = lgcn_launch_linear(qa, st)) return rc;
+    if (int rc = lgcn_launch_linear(qa, fk->on(0, st))) return rc;
     q = A0; qidx = hi;
   } else {
     LinearArgs qp = with_w(pair_rows(agts_in, hi, w.qw, w.qg, w.qb, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P2), 1);
-    if (int rc = lgcn_launch_linear(qp, st)) return rc;
+    if (int rc = lgcn_launch_linear(qp, fk->on(0, st))) return rc;
     q = P2; qidx = nullptr;
   }
+  // agt(agts), the Linear of lanegcn.py:702
+  LinearArgs ag = with_w(agt_rows(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1), 6);
+  if (int rc = lgcn_launch_linear(ag, fk->on(1, st))) return rc;
+  // dist = relu(GN(L(relu(L2(agt_ctrs[hi] - ctx_ctrs[wi])))))                      lanegcn.py:693-694
+  if (int rc = lgcn_launch_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, n_pairs_dev, st)) return rc;
+  LinearArgs d2 = with_w(pair_rows(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1), 0);
+  if (int rc = lgcn_launch_linear(d2, st)) return rc;
+  if (fk->join(0, st)) return -2;
   // ctx = L(relu(GN(L384(cat(dist, query, ctx[wi])))))  — split-K over the three sources, no cat   :698-700
   LinearArgs c0 = with_w(pair_rows(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0), 2);
   c0.n_src = 3;
@@ -418,9 +427,8 @@ int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, cons
   if (int rc = lgcn_launch_linear(c0, st)) return rc;
   LinearArgs c1 = with_w(pair_rows(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1), 5);
   if (int rc = lgcn_launch_linear(c1, st)) return rc;
+  if (fk->join(1, st)) return -2;
   // agts = relu(GN(agt(agts) + scatter(ctx by hi)))                                                  :702-705
-  LinearArgs ag = with_w(agt_rows(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1), 6);
-  if (int rc = lgcn_launch_linear(ag, st)) return rc;
   if (int rc = lgcn_launch_segsum_gn_relu(A1, P1, rowptr, w.ng, w.nb, A0, n_agt, n_agt_dev, st)) return rc;
   // agts = relu(GN(linear(agts)) + res)                                                              :707-709
   LinearArgs l = with_w(agt_rows(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out), 7);
@@ -441,5 +449,5 @@ extern "C" int lgcn_att_forward(const float* agts_in, float* agts_out, const flo
   if (pre)
     if (int rc = lgcn_att_split_weights(wpack, WH, WL, st)) return rc;
   return lgcn_att_layer(agts_in, agts_out, ctx, agt_ctrs, ctx_ctrs, hi, wi, rowptr, n_agt, nullptr, n_ctx, n_pairs, nullptr,
-                        wpack, pre ? WH : nullptr, pre ? WL : nullptr, workspace, st);
+                        wpack, pre ? WH : nullptr, pre ? WL : nullptr, workspace, st, nullptr);
 }

@@ -78,6 +78,26 @@ static inline cudaError_t lgcn_launch_pdl(void (*kernel)(KArgs...), unsigned gri
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Optional parallel branches inside one library call: independent kernels are forked from the call's stream onto up to two
+// caller-provided auxiliary streams and joined before anything reads their results / before the call returns (plain
+// event record + wait: capturable, the branches become parallel paths of the CUDA graph).  aux[i] == NULL: stay serial.
+struct LgcnFork {
+  cudaStream_t aux[2];
+  cudaEvent_t ev[3];   // [0] fork point on the main stream, [1 + i] end of branch i
+  bool has(int i) const { return aux[i] != nullptr; }
+  int fork(int i, cudaStream_t st) const {
+    if (!has(i)) return 0;
+    if (cudaEventRecord(ev[0], st) != cudaSuccess || cudaStreamWaitEvent(aux[i], ev[0], 0) != cudaSuccess) return -2;
+    return 0;
+  }
+  int join(int i, cudaStream_t st) const {
+    if (!has(i)) return 0;
+    if (cudaEventRecord(ev[1 + i], aux[i]) != cudaSuccess || cudaStreamWaitEvent(st, ev[1 + i], 0) != cudaSuccess) return -2;
+    return 0;
+  }
+  cudaStream_t on(int i, cudaStream_t st) const { return has(i) ? aux[i] : st; }
+};
+
 static inline int64_t lgcn_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned lgcn_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 

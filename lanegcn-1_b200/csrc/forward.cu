@@ -5,6 +5,8 @@
 // (the reference synchronises once per scene per Att layer: lanegcn.py:680-681).
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 #define CC ((int64_t)LGCN_C * LGCN_C)
@@ -16,12 +18,37 @@ int lgcn_att_split_weights(const float* wpack, float* WH, float* WL, cudaStream_
 int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, const float* agt_ctrs, const float* ctx_ctrs,
                    const int32_t* hi, const int32_t* wi, const int32_t* rowptr, int64_t n_agt, const int32_t* n_agt_dev,
                    int64_t n_ctx, int64_t n_pairs, const int32_t* n_pairs_dev, const float* wpack, const float* WH,
-                   const float* WL, void* workspace, cudaStream_t st);
+                   const float* WL, void* workspace, cudaStream_t st, const LgcnFork* fk);
 int lgcn_laneconv_stack_presplit(float* feat, float* other, float* xa, void* plan, int64_t n_edges, int n_keys,
                                  int n_blocks, const float* wpack, const float* w_hi, const float* w_lo, int64_t n_nodes,
                                  const int32_t* n_dev, cudaStream_t st);
 
 namespace {
+
+// ---- fork / join events of the optional parallel branches (LgcnForwardArgs.aux_streams): three per device, created on
+// first use and kept for the life of the process like the cached function attributes (they carry no data: a record /
+// wait pair only orders streams, and inside a capture it only adds graph edges)
+constexpr int kMaxDev = 64;
+cudaEvent_t g_fork_ev[kMaxDev][3];
+bool g_fork_ready[kMaxDev];
+std::mutex g_fork_mu;
+int fork_of(const LgcnForwardArgs& a, LgcnFork* fk) {
+  memset(fk, 0, sizeof(*fk));
+  if (!a.aux_streams[0] && !a.aux_streams[1]) return 0;
+  int dev = 0;
+  LGCN_CUDA_OK(cudaGetDevice(&dev));
+  LGCN_CHECK_ARG(dev >= 0 && dev < kMaxDev, "forward: device %d", dev);
+  {
+    std::lock_guard<std::mutex> lock(g_fork_mu);
+    if (!g_fork_ready[dev]) {
+      for (int i = 0; i < 3; ++i) LGCN_CUDA_OK(cudaEventCreateWithFlags(&g_fork_ev[dev][i], cudaEventDisableTiming));
+      g_fork_ready[dev] = true;
+    }
+  }
+  for (int i = 0; i < 2; ++i) fk->aux[i] = (cudaStream_t)a.aux_streams[i];
+  for (int i = 0; i < 3; ++i) fk->ev[i] = g_fork_ev[dev][i];
+  return 0;
+}
 
 // ---- tf32 hi / lo images of the weights (float offsets into `prepared`)
 struct Prepared {
@@ -206,9 +233,30 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
   void* att_ws = ws + L.att_ws;
   int32_t* p_tot = (int32_t*)(ws + L.p_tot);
   const int n_seg = 2 * L.n_keys * a.cap_scenes;
+  LgcnFork fk;
+  if (int rc = fork_of(a, &fk)) return rc;
 
   if (a.stages & LGCN_STAGE_GRAPH) {
     if (int rc = lgcn_zero_async(a.status, 8 * sizeof(int32_t), st)) return rc;
+    // the three pair lists depend on the centres only (lanegcn.py:672-689; both Att layers of a block share theirs) and
+    // not on the edge lists: with an auxiliary stream they are built beside the CSR / plan chain
+    if (fk.fork(0, st)) return -2;
+    {
+      cudaStream_t ps = fk.on(0, st);
+      const float* agt_c[3] = {a.node_ctrs, a.actor_ctrs, a.actor_ctrs};
+      const float* ctx_c[3] = {a.actor_ctrs, a.node_ctrs, a.actor_ctrs};
+      const int32_t* agt_o[3] = {a.node_off, a.actor_off, a.actor_off};
+      const int32_t* ctx_o[3] = {a.actor_off, a.node_off, a.actor_off};
+      const int64_t n_agt[3] = {N, A, A};
+      const int32_t* n_agt_dev[3] = {n_nodes, n_actors, n_actors};
+      const int64_t n_ctx[3] = {A, N, A};
+      for (int i = 0; i < 3; ++i)
+        if (int rc = lgcn_launch_pairs(agt_c[i], ctx_c[i], agt_o[i], ctx_o[i], a.cap_scenes, n_agt[i], n_agt_dev[i],
+                                       a.dist_th[i], a.keep_pair_quirk, (int32_t*)(ws + L.p_rowptr[i]), ws + L.p_ws[i],
+                                       a.cap_pairs[i], (int32_t*)(ws + L.p_hi[i]), (int32_t*)(ws + L.p_wi[i]), p_tot + i,
+                                       a.status, a.status + 1 + i, LGCN_ST_OVERFLOW_A2M << i, LGCN_ST_EMPTY_A2M << i, n_ctx[i], ps))
+          return rc;
+    }
     // utils.to_long + the offset / cat loops of graph_gather (lanegcn.py:191-208)
     if (int rc = lgcn_offset_indices(a.local_idx, a.idx_bytes, a.segs, a.segs + n_seg + 1, n_seg, a.cap_index, e64, stream))
       return rc;
@@ -217,20 +265,7 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
                                            ws + L.csr_ws, a.status + 4, st))
       return rc;
     if (int rc = lgcn_launch_plan_build(rowptr, col, L.n_keys, N, n_nodes, L.E_cap, plan, st)) return rc;
-    // the three pair lists depend on the centres only (lanegcn.py:672-689); both Att layers of a block share theirs
-    const float* agt_c[3] = {a.node_ctrs, a.actor_ctrs, a.actor_ctrs};
-    const float* ctx_c[3] = {a.actor_ctrs, a.node_ctrs, a.actor_ctrs};
-    const int32_t* agt_o[3] = {a.node_off, a.actor_off, a.actor_off};
-    const int32_t* ctx_o[3] = {a.actor_off, a.node_off, a.actor_off};
-    const int64_t n_agt[3] = {N, A, A};
-    const int32_t* n_agt_dev[3] = {n_nodes, n_actors, n_actors};
-    const int64_t n_ctx[3] = {A, N, A};
-    for (int i = 0; i < 3; ++i)
-      if (int rc = lgcn_launch_pairs(agt_c[i], ctx_c[i], agt_o[i], ctx_o[i], a.cap_scenes, n_agt[i], n_agt_dev[i],
-                                     a.dist_th[i], a.keep_pair_quirk, (int32_t*)(ws + L.p_rowptr[i]), ws + L.p_ws[i],
-                                     a.cap_pairs[i], (int32_t*)(ws + L.p_hi[i]), (int32_t*)(ws + L.p_wi[i]), p_tot + i,
-                                     a.status, a.status + 1 + i, LGCN_ST_OVERFLOW_A2M << i, LGCN_ST_EMPTY_A2M << i, n_ctx[i], st))
-        return rc;
+    if (fk.join(0, st)) return -2;
   }
 
   if (a.stages & LGCN_STAGE_MAPNET) {
@@ -264,7 +299,7 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
     for (int i = 0; i < 2; ++i)
       if (int rc = lgcn_att_layer(i ? a.nodes : t0, a.nodes, a.actors, a.node_ctrs, a.actor_ctrs, (int32_t*)(ws + L.p_hi[0]),
                                   (int32_t*)(ws + L.p_wi[0]), (int32_t*)(ws + L.p_rowptr[0]), N, n_nodes, A,
-                                  a.cap_pairs[0], p_tot + 0, a.w.att[i], prep + P.att_hi[i], prep + P.att_lo[i], att_ws, st))
+                                  a.cap_pairs[0], p_tot + 0, a.w.att[i], prep + P.att_hi[i], prep + P.att_lo[i], att_ws, st, &fk))
         return rc;
   }
 
@@ -278,7 +313,7 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
       if (int rc = lgcn_att_layer(a.actors, a.actors, a.nodes, a.actor_ctrs, a.node_ctrs, (int32_t*)(ws + L.p_hi[1]),
                                   (int32_t*)(ws + L.p_wi[1]), (int32_t*)(ws + L.p_rowptr[1]), A, n_actors, N,
                                   a.cap_pairs[1], p_tot + 1, a.w.att[2 + i], prep + P.att_hi[2 + i], prep + P.att_lo[2 + i],
-                                  att_ws, st))
+                                  att_ws, st, &fk))
         return rc;
 
   if (a.stages & LGCN_STAGE_A2A)
@@ -286,7 +321,7 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
       if (int rc = lgcn_att_layer(a.actors, a.actors, a.actors, a.actor_ctrs, a.actor_ctrs, (int32_t*)(ws + L.p_hi[2]),
                                   (int32_t*)(ws + L.p_wi[2]), (int32_t*)(ws + L.p_rowptr[2]), A, n_actors, A,
                                   a.cap_pairs[2], p_tot + 2, a.w.att[4 + i], prep + P.att_hi[4 + i], prep + P.att_lo[4 + i],
-                                  att_ws, st))
+                                  att_ws, st, &fk))
         return rc;
   return 0;
 #else

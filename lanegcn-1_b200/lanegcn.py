@@ -1387,6 +1387,14 @@ class Net(nn.Module):
             else:   # ONE kernel, straight from the step-major histories (the transpose of actor_gather is folded in)
                 self.actor_net.forward_ntc(slot.actor_feats, out=slot.actors, n_dev=n_act_dev)
 
+        # two more high-priority streams the library may fork independent kernels onto (pair lists beside the CSR build,
+        # the query / agt Linears of an Att layer beside its pair-side chain); joined back inside the call
+        if os.environ.get("LGCN_AUX_STREAMS", "1") != "0":
+            a.aux_streams[0] = _side_stream(dev, "aux0", priority=-1).cuda_stream
+            a.aux_streams[1] = _side_stream(dev, "aux1", priority=-1).cuda_stream
+        else:
+            a.aux_streams[0] = a.aux_streams[1] = None
+
         def run(stages):
             a.stages = stages
             _C.check(lib.lgcn_forward(ctypes.byref(a), cur.cuda_stream), "forward")
