@@ -1379,14 +1379,6 @@ class Net(nn.Module):
         side.wait_stream(cur)
         torch_blocks = os.environ.get("LGCN_TORCH_BLOCKS", "0") == "1"
         n_act_dev = slot.dims[1:]
-        with torch.cuda.stream(side):   # ActorNet is independent of the map: a parallel branch      lanegcn.py:129-131
-            if torch_blocks:
-                _C.check(lib.lgcn_actor_gather(slot.actor_feats.data_ptr(), slot.actors_t.data_ptr(), slot.caps.actors, 20, 3,
-                                               side.cuda_stream), "actor_gather")
-                slot.actors.copy_(self.actor_net(slot.actors_t))
-            else:   # ONE kernel, straight from the step-major histories (the transpose of actor_gather is folded in)
-                self.actor_net.forward_ntc(slot.actor_feats, out=slot.actors, n_dev=n_act_dev)
-
         # two more high-priority streams the library may fork independent kernels onto (pair lists beside the CSR build,
         # the query / agt Linears of an Att layer beside its pair-side chain); joined back inside the call
         if os.environ.get("LGCN_AUX_STREAMS", "1") != "0":
@@ -1399,7 +1391,19 @@ class Net(nn.Module):
             a.stages = stages
             _C.check(lib.lgcn_forward(ctypes.byref(a), cur.cuda_stream), "forward")
 
-        run(_C.STAGE_GRAPH | _C.STAGE_MAPNET)                                                 # :134-135
+        actor_first = os.environ.get("LGCN_ACTOR_FIRST", "1") == "1"   # either order gives the same step (measured)
+        if not actor_first:
+            run(_C.STAGE_GRAPH | _C.STAGE_MAPNET)                                             # :134-135
+        with torch.cuda.stream(side):   # ActorNet is independent of the map: a parallel branch      lanegcn.py:129-131
+            if torch_blocks:
+                _C.check(lib.lgcn_actor_gather(slot.actor_feats.data_ptr(), slot.actors_t.data_ptr(), slot.caps.actors, 20, 3,
+                                               side.cuda_stream), "actor_gather")
+                slot.actors.copy_(self.actor_net(slot.actors_t))
+            else:   # ONE kernel, straight from the step-major histories (the transpose of actor_gather is folded in)
+                self.actor_net.forward_ntc(slot.actor_feats, out=slot.actors, n_dev=n_act_dev)
+
+        if actor_first:
+            run(_C.STAGE_GRAPH | _C.STAGE_MAPNET)
         cur.wait_stream(side)
         if taps is None:
             run(_C.STAGE_A2M | _C.STAGE_M2M | _C.STAGE_M2A | _C.STAGE_A2A)                    # :138-141
