@@ -339,6 +339,13 @@ int lgcn_actor_net_pack(const float* const* h_conv_w, const float* const* h_gamm
                         float* wpack, void* stream);
 int lgcn_actor_net(const float* feats, const float* wpack, float* out, int64_t n_actors, const int32_t* n_actors_dev,
                    void* stream);
+/* The same network with its output Res1d (46 % of the FLOPs: two 128 -> 128, k = 3 convs over all 20 steps) on the tensor
+ * core: the fp32 kernel stops after the feature pyramid, each conv is a Linear with three K = 128 sources (a row and its
+ * two neighbours in time, zero rows at an actor's ends; 3xTF32 like every Linear of the path), GroupNorm over an actor's
+ * [128 x 20] outputs in a small kernel.  Same wpack; tcgen05 engine only.  workspace: lgcn_actor_net_tc_workspace_bytes. */
+int64_t lgcn_actor_net_tc_workspace_bytes(int64_t n_actors);
+int lgcn_actor_net_tc(const float* feats, const float* wpack, float* out, int64_t n_actors, const int32_t* n_actors_dev,
+                      void* workspace, void* stream);
 
 /* ------------------------------------------------------------------ PredNet + AttDest + sort + world transform, ONE kernel
  * (lanegcn.py:575-631, 713-737, 145-150).  actors [n,128], actor_ctrs [n,2] -> cls [n,6] (descending), reg [n,6,30,2]

@@ -72,6 +72,8 @@ _SIGS = {
     "lgcn_actor_net_wpack_floats": (_i64, []),
     "lgcn_actor_net_pack": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "lgcn_actor_net": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "lgcn_actor_net_tc_workspace_bytes": (_i64, [_i64]),
+    "lgcn_actor_net_tc": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "lgcn_pred_net_wpack_floats": (_i64, []),
     "lgcn_pred_net_pack": (_i32, [_vp, _vp, _vp]),
     "lgcn_pred_net": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -166,16 +166,30 @@ class ActorNet(nn.Module):
             self._keep = ps   # converted copies must outlive the asynchronous packing kernels
         return self._pp.get(params, lib.lgcn_actor_net_wpack_floats(), write)
 
-    def forward_ntc(self, feats, out=None, n_dev=None):
-        """feats [A, 20, 3] (step-major, as the dataset stores the histories) -> [A, n_actor]; ONE kernel."""
+    @staticmethod
+    def tensor_core_path() -> bool:
+        """The output Res1d on the tensor core (lgcn_actor_net_tc) unless LGCN_ACTOR=fp32 or the SIMT engine is selected."""
+        return os.environ.get("LGCN_ACTOR", "tc") != "fp32" and _C.lib().lgcn_get_gemm_engine() == 1
+
+    def forward_ntc(self, feats, out=None, n_dev=None, ws=None):
+        """feats [A, 20, 3] (step-major, as the dataset stores the histories) -> [A, n_actor].  One fp32 kernel, or (default
+        on the tcgen05 engine) the fp32 kernel up to the feature pyramid + the output Res1d as two tensor-core Linears;
+        ``ws``: workspace of lgcn_actor_net_tc_workspace_bytes(A) (static buffers of a graph-captured slot)."""
         if self.output.conv1.weight.shape[0] != 128 or feats.shape[1:] != (20, 3):
             raise RuntimeError("lanegcn_b200: the ActorNet kernel is built for n_actor = 128 and [A, 20, 3] inputs")
         feats = feats if (feats.dtype == torch.float32 and feats.is_contiguous()) else feats.float().contiguous()
+        lib, n = _C.lib(), feats.shape[0]
         if out is None:
-            out = torch.empty(feats.shape[0], 128, dtype=torch.float32, device=feats.device)
+            out = torch.empty(n, 128, dtype=torch.float32, device=feats.device)
         with torch.cuda.device(feats.device):
-            _C.check(_C.lib().lgcn_actor_net(feats.data_ptr(), self.wpack().data_ptr(), out.data_ptr(), feats.shape[0],
-                                             _C.ptr(n_dev), _C.stream_ptr()), "actor_net")
+            if self.tensor_core_path():
+                if ws is None:
+                    ws = torch.empty(lib.lgcn_actor_net_tc_workspace_bytes(n), dtype=torch.uint8, device=feats.device)
+                _C.check(lib.lgcn_actor_net_tc(feats.data_ptr(), self.wpack().data_ptr(), out.data_ptr(), n, _C.ptr(n_dev),
+                                               ws.data_ptr(), _C.stream_ptr()), "actor_net_tc")
+            else:
+                _C.check(lib.lgcn_actor_net(feats.data_ptr(), self.wpack().data_ptr(), out.data_ptr(), n, _C.ptr(n_dev),
+                                            _C.stream_ptr()), "actor_net")
         return out
 
     def forward(self, actors):

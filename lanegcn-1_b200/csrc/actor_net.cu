@@ -281,9 +281,12 @@ __device__ __forceinline__ void res1d(const float* x, float* h, float* y, float*
   }
 }
 
+// FPN_ONLY: stop after the feature pyramid and write its [A][20][128] rows to `out`; the output Res1d (46 % of the
+// network's FLOPs: two 128 -> 128 k=3 convs over all 20 steps) then runs on the tensor core (lgcn_actor_net_tc below).
+template <bool FPN_ONLY>
 __global__ void __launch_bounds__(kThreads, 2)
-k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __restrict__ pack, float* __restrict__ out /* [A][128] */,
-            int64_t a_cap, const int32_t* __restrict__ a_dev) {
+k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __restrict__ pack,
+            float* __restrict__ out /* [A][128], or [A][20][128] with FPN_ONLY */, int64_t a_cap, const int32_t* __restrict__ a_dev) {
   extern __shared__ __align__(16) float sm[];
   const int64_t A = lgcn_devn(a_dev, a_cap);
   const int64_t a0 = (int64_t)blockIdx.x * kActors;
@@ -326,6 +329,14 @@ k_actor_net(const float* __restrict__ feats /* [A][20][3] */, const float* __res
     conv<32, 128, 3, 1, 20, 10, 2>(F0, R, l0.w, wst);
     gn_apply<128, 20>(R, P, l0.gamma, l0.beta, nullptr, GN_ACCUM, stats);
   }
+  if constexpr (FPN_ONLY) {
+    for (int i = threadIdx.x; i < kActors * 20 * 32; i += kThreads) {
+      const int g = i / (20 * 32), l = (i / 32) % 20, c = (i & 31) * 4;
+      if (a0 + g < A)
+        *reinterpret_cast<float4*>(out + ((a0 + g) * 20 + l) * LGCN_C + c) = lds4(P + ((int64_t)g * 22 + l + 1) * 128 + c);
+    }
+    return;
+  }
   // output Res1d, last step only                                                                  lanegcn.py:262
   res1d<128, 128, 1, 20, 10, 18, 19, -1, 2>(P, Q, R, nullptr, R, pack, wst, stats);
   for (int i = threadIdx.x; i < kActors * 32; i += kThreads) {
@@ -343,11 +354,98 @@ __global__ void k_pack_conv(const float* __restrict__ w, float* __restrict__ dst
   dst[i] = ci < cin ? w[((int64_t)co * cin + ci) * k + kk] : 0.f;
 }
 
+// ---- output Res1d on the tensor core: a k=3 conv over rows (actor, step) is a Linear with three K=128 sources, the
+// row itself and its two neighbours (row gathers; -1 = the zero pad at an actor's first / last step)
+// conv.weight [128][128][3] -> [co][slot][ci] with slot 0 = centre tap, 1 = previous step, 2 = next step
+__global__ void k_pack_conv3(const float* __restrict__ w, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 3 * 128) return;
+  const int ci = i & 127, slot = (i >> 7) % 3, co = i / 384;
+  const int tap = slot == 0 ? 1 : slot == 1 ? 0 : 2;
+  dst[i] = w[((int64_t)co * 128 + ci) * 3 + tap];
+}
+__global__ void k_actor_conv_idx(int32_t* __restrict__ prev, int32_t* __restrict__ next, int64_t rows) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int l = (int)(r % 20);
+  prev[r] = l == 0 ? -1 : (int32_t)r - 1;
+  next[r] = l == 19 ? -1 : (int32_t)r + 1;
+}
+// GroupNorm(1 group over the [128 x 20] outputs of an actor, two-pass like gn_apply) of the raw conv rows h [A*20][128].
+// LAST = false: h <- relu(norm * gamma + beta) in place (bn1 of the output Res1d, layers.py:176-178);
+// LAST = true : out[a] = relu(norm(h[a, 19]) * gamma + beta + res[a, 19])   (bn2 + shortcut + ReLU, last step only:
+//               lanegcn.py:262).  One CTA of 256 threads per actor.
+template <bool LAST>
+__global__ void __launch_bounds__(256)
+k_actor_gn(float* __restrict__ h, const float* __restrict__ gamma, const float* __restrict__ beta,
+           const float* __restrict__ res, float* __restrict__ out, int64_t a_cap, const int32_t* __restrict__ a_dev) {
+  __shared__ float red[8];
+  const int64_t a = blockIdx.x;
+  if (a >= lgcn_devn(a_dev, a_cap)) return;
+  float4* row = reinterpret_cast<float4*>(h + a * 20 * LGCN_C);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 v[3];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    v[j] = i < 640 ? row[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float mean = tot * (1.0f / 2560.0f);
+  __syncthreads();
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (threadIdx.x + 256 * j < 640) {
+      const float a0 = v[j].x - mean, a1 = v[j].y - mean, a2 = v[j].z - mean, a3 = v[j].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  float qt = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) qt += red[w];
+  const float rstd = 1.0f / sqrtf(qt * (1.0f / 2560.0f) + LGCN_GN_EPS);
+  if (!LAST) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < 640) {
+        const int c = (i & 31) * 4;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+        row[i] = relu4(make_float4((v[j].x - mean) * rstd * ga.x + be.x, (v[j].y - mean) * rstd * ga.y + be.y,
+                                   (v[j].z - mean) * rstd * ga.z + be.z, (v[j].w - mean) * rstd * ga.w + be.w));
+      }
+    }
+  } else if (threadIdx.x < 32) {
+    const int c = threadIdx.x * 4;
+    const float4 x = row[19 * 32 + threadIdx.x], r = *reinterpret_cast<const float4*>(res + (a * 20 + 19) * LGCN_C + c);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    *reinterpret_cast<float4*>(out + a * LGCN_C + c) =
+        relu4(make_float4((x.x - mean) * rstd * ga.x + be.x + r.x, (x.y - mean) * rstd * ga.y + be.y + r.y,
+                          (x.z - mean) * rstd * ga.z + be.z + r.z, (x.w - mean) * rstd * ga.w + be.w + r.w));
+  }
+}
+
+// float offsets of the tensor-core images behind the 20 fp32 layers of the pack
+constexpr int64_t kOffW3 = spec_offset(20);                        // 2 x [128][3][128] (output.conv1, output.conv2)
+constexpr int64_t kOffHi = kOffW3 + 2 * 128 * 384;                 // tf32 hi images: 6 blocks [128][128]
+constexpr int64_t kOffLo = kOffHi + 6 * 128 * 128;                 // lo images
+constexpr int64_t kPackFloats = kOffLo + 6 * 128 * 128;
+
 std::atomic<int> g_attr[64];
 
 }  // namespace
 
-extern "C" int64_t lgcn_actor_net_wpack_floats(void) { return spec_offset(20); }
+extern "C" int64_t lgcn_actor_net_wpack_floats(void) { return kPackFloats; }
 
 extern "C" int lgcn_actor_net_pack(const float* const* h_conv_w, const float* const* h_gamma, const float* const* h_beta,
                                    float* wpack, void* stream) {
@@ -363,17 +461,35 @@ extern "C" int lgcn_actor_net_pack(const float* const* h_conv_w, const float* co
     LGCN_CUDA_OK(cudaMemcpyAsync(dst + n, h_gamma[i], s.cout * 4, cudaMemcpyDeviceToDevice, st));
     LGCN_CUDA_OK(cudaMemcpyAsync(dst + n + s.cout, h_beta[i], s.cout * 4, cudaMemcpyDeviceToDevice, st));
   }
+#if LGCN_HAVE_TC
+  // the two convs of the output Res1d once more as three-source Linear weights + their tf32 hi / lo images
+  LgcnSplitList sl;
+  sl.n_blocks = 6;
+  for (int j = 0; j < 2; ++j) {
+    float* w3 = wpack + kOffW3 + (int64_t)j * 128 * 384;
+    k_pack_conv3<<<lgcn_cdiv(128 * 384, 256), 256, 0, st>>>(h_conv_w[18 + j], w3);
+    LGCN_LAUNCH_OK();
+    for (int sidx = 0; sidx < 3; ++sidx) {
+      sl.p[3 * j + sidx] = w3 + sidx * 128;
+      sl.ldw[3 * j + sidx] = 384;
+    }
+  }
+  if (int rc = lgcn_split_blocks_many(sl, wpack + kOffHi, wpack + kOffLo, st)) return rc;
+#endif
   return 0;
 }
 
-int lgcn_launch_actor_net(const float* feats, const float* wpack, float* out, int64_t a_cap, const int32_t* a_dev,
-                          cudaStream_t st) {
+static int launch_actor_net(const float* feats, const float* wpack, float* out, int64_t a_cap, const int32_t* a_dev,
+                            bool fpn_only, cudaStream_t st) {
   if (a_cap <= 0) return 0;
   int dev = 0;
   LGCN_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && g_attr[dev].exchange(1) == 0)
-    LGCN_CUDA_OK(cudaFuncSetAttribute(k_actor_net, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  k_actor_net<<<lgcn_cdiv(a_cap, kActors), kThreads, kSmemBytes, st>>>(feats, wpack, out, a_cap, a_dev);
+  if (dev >= 0 && dev < 64 && g_attr[dev].exchange(1) == 0) {
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_actor_net<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_actor_net<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  }
+  if (fpn_only) k_actor_net<true><<<lgcn_cdiv(a_cap, kActors), kThreads, kSmemBytes, st>>>(feats, wpack, out, a_cap, a_dev);
+  else k_actor_net<false><<<lgcn_cdiv(a_cap, kActors), kThreads, kSmemBytes, st>>>(feats, wpack, out, a_cap, a_dev);
   LGCN_LAUNCH_OK();
   return 0;
 }
@@ -382,5 +498,57 @@ extern "C" int lgcn_actor_net(const float* feats, const float* wpack, float* out
                               const int32_t* n_actors_dev, void* stream) {
   LGCN_CHECK_ARG(n_actors >= 0, "actor_net: n_actors %lld", (long long)n_actors);
   LGCN_CHECK_ARG(n_actors == 0 || (feats && wpack && out), "actor_net: NULL argument");
-  return lgcn_launch_actor_net(feats, wpack, out, n_actors, n_actors_dev, (cudaStream_t)stream);
+  return launch_actor_net(feats, wpack, out, n_actors, n_actors_dev, false, (cudaStream_t)stream);
+}
+
+// ---- the same network with the output Res1d on the tensor core (3xTF32 like every Linear of the path):
+//   k_actor_net<FPN_ONLY> -> fpn [A*20,128]  ->  conv1 = 3-source Linear  ->  GN + ReLU per actor  ->  conv2  ->
+//   GN + shortcut + ReLU at the last step -> out [A,128]
+// workspace: fpn | h1 | h2 [A*20,128] fp32 each | prev, next int32 [A*20]
+LinearArgs lgcn_lin1(const float* x, const int32_t* idx, const float* W, const float* gamma, const float* beta,
+                     const float* res, int flags, float* out, int64_t m, const int32_t* m_dev);
+
+extern "C" int64_t lgcn_actor_net_tc_workspace_bytes(int64_t n_actors) {
+  const int64_t rows = n_actors * 20;
+  return 3 * lgcn_align_up(rows * LGCN_C * 4, 1024) + 2 * lgcn_align_up(rows * 4, 1024) + 1024;
+}
+
+extern "C" int lgcn_actor_net_tc(const float* feats, const float* wpack, float* out, int64_t n_actors,
+                                 const int32_t* n_actors_dev, void* workspace, void* stream) {
+#if LGCN_HAVE_TC
+  LGCN_CHECK_ARG(n_actors >= 0 && n_actors * 20 < ((int64_t)1 << 31), "actor_net_tc: n_actors %lld", (long long)n_actors);
+  LGCN_CHECK_ARG(n_actors == 0 || (feats && wpack && out && workspace), "actor_net_tc: NULL argument");
+  LGCN_CHECK_ARG(lgcn_get_gemm_engine() == 1, "actor_net_tc needs the tcgen05 engine (lgcn_actor_net is the fp32 kernel)");
+  if (n_actors == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = n_actors * 20, fb = lgcn_align_up(rows * LGCN_C * 4, 1024), ib = lgcn_align_up(rows * 4, 1024);
+  float* buf[3] = {(float*)workspace, (float*)((char*)workspace + fb), (float*)((char*)workspace + 2 * fb)};   // fpn, h1, h2
+  int32_t* prev = (int32_t*)((char*)workspace + 3 * fb);
+  int32_t* next = (int32_t*)((char*)workspace + 3 * fb + ib);
+  k_actor_conv_idx<<<lgcn_cdiv(rows, 256), 256, 0, st>>>(prev, next, rows);
+  LGCN_LAUNCH_OK();
+  if (int rc = launch_actor_net(feats, wpack, buf[0], n_actors, n_actors_dev, true, st)) return rc;
+  for (int j = 0; j < 2; ++j) {   // output.conv1 / bn1 / ReLU, then output.conv2 / bn2 + shortcut + ReLU at the last step
+    const Spec sp = spec(18 + j);
+    const float* gamma = wpack + spec_offset(18 + j) + (int64_t)sp.k * cin_padded(sp.cin) * sp.cout;
+    const float* beta = gamma + sp.cout;
+    // rows past the live actors (n_actors is a capacity when n_actors_dev is given) are computed too: row-independent
+    LinearArgs la = lgcn_lin1(buf[j], nullptr, wpack + kOffW3 + (int64_t)j * 128 * 384, nullptr, nullptr, nullptr, 0,
+                              buf[j + 1], rows, nullptr);
+    la.n_src = 3;
+    la.a[1] = buf[j]; la.idx[1] = prev;
+    la.a[2] = buf[j]; la.idx[2] = next;
+    la.w_hi = wpack + kOffHi + (int64_t)j * 3 * 128 * 128;
+    la.w_lo = wpack + kOffLo + (int64_t)j * 3 * 128 * 128;
+    if (int rc = lgcn_launch_linear(la, st)) return rc;
+    if (j == 0) k_actor_gn<false><<<(unsigned)n_actors, 256, 0, st>>>(buf[1], gamma, beta, nullptr, nullptr, n_actors, n_actors_dev);
+    else k_actor_gn<true><<<(unsigned)n_actors, 256, 0, st>>>(buf[2], gamma, beta, buf[0], out, n_actors, n_actors_dev);
+    LGCN_LAUNCH_OK();
+  }
+  return 0;
+#else
+  (void)feats; (void)wpack; (void)out; (void)n_actors; (void)n_actors_dev; (void)workspace; (void)stream;
+  LGCN_CHECK_ARG(false, "actor_net_tc: built without the tcgen05 engine");
+  return -1;
+#endif
 }

@@ -97,6 +97,7 @@ class Slot:
             raise RuntimeError("lgcn forward_workspace_bytes: " + lib.lgcn_last_error().decode())
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         a.workspace = self.ws.data_ptr()
+        self.actor_ws = torch.zeros(lib.lgcn_actor_net_tc_workspace_bytes(A), dtype=torch.uint8, device=dev)
         # ---- execution state
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_kernels = 0                       # lgcn kernels per replay (counted at capture)

@@ -1400,7 +1400,7 @@ class Net(nn.Module):
                                                side.cuda_stream), "actor_gather")
                 slot.actors.copy_(self.actor_net(slot.actors_t))
             else:   # ONE kernel, straight from the step-major histories (the transpose of actor_gather is folded in)
-                self.actor_net.forward_ntc(slot.actor_feats, out=slot.actors, n_dev=n_act_dev)
+                self.actor_net.forward_ntc(slot.actor_feats, out=slot.actors, n_dev=n_act_dev, ws=slot.actor_ws)
 
         if actor_first:
             run(_C.STAGE_GRAPH | _C.STAGE_MAPNET)

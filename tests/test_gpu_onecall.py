@@ -193,8 +193,10 @@ def test_second_device_if_present(lib):
 
 
 # --------------------------------------------------------------------------- ActorNet / PredNet kernels (f2, f3)
+@pytest.mark.parametrize("path", ["tc", "fp32"])
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 64, 257])
-def test_actor_net_kernel_vs_oracle_and_torch(cuda, lib, net, n):
+def test_actor_net_kernel_vs_oracle_and_torch(cuda, lib, net, n, path, monkeypatch):
+    monkeypatch.setenv("LGCN_ACTOR", path)   # tc: output Res1d on the tensor core (default); fp32: the single fp32 kernel
     g = torch.Generator().manual_seed(n)
     feats = torch.randn(n, 20, 3, generator=g) * 0.5
     feats[:, :, 2] = (torch.rand(n, 20, generator=g) > 0.2).float()
