@@ -420,16 +420,24 @@ int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, cons
   if (int rc = lgcn_launch_linear(d2, st)) return rc;
   if (fk->join(0, st)) return -2;
   // ctx = L(relu(GN(L384(cat(dist, query, ctx[wi])))))  — split-K over the three sources, no cat   :698-700
+  // with pre-split weights ctx.1 is chained inside ctx.0's kernel (its block follows ctx.0's three in WH / WL)
+  const bool chain_c1 = pre && !(lgcn_debug_get() & 65536);
   LinearArgs c0 = with_w(pair_rows(P1, nullptr, w.c0w, w.c0g, w.c0b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P0), 2);
   c0.n_src = 3;
   c0.a[1] = q; c0.idx[1] = qidx;
   c0.a[2] = ctx; c0.idx[2] = wi;
+  c0.chain = chain_c1 ? 1 : 0;
+  c0.flags2 = 0;
   if (int rc = lgcn_launch_linear(c0, st)) return rc;
-  LinearArgs c1 = with_w(pair_rows(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1), 5);
-  if (int rc = lgcn_launch_linear(c1, st)) return rc;
+  const float* ctx_out = P0;   // P0 is free again: dist.2 has consumed the K=2 head's rows
+  if (!chain_c1) {
+    LinearArgs c1 = with_w(pair_rows(P0, nullptr, w.c1w, nullptr, nullptr, nullptr, 0, P1), 5);
+    if (int rc = lgcn_launch_linear(c1, st)) return rc;
+    ctx_out = P1;
+  }
   if (fk->join(1, st)) return -2;
   // agts = relu(GN(agt(agts) + scatter(ctx by hi)))                                                  :702-705
-  if (int rc = lgcn_launch_segsum_gn_relu(A1, P1, rowptr, w.ng, w.nb, A0, n_agt, n_agt_dev, st)) return rc;
+  if (int rc = lgcn_launch_segsum_gn_relu(A1, ctx_out, rowptr, w.ng, w.nb, A0, n_agt, n_agt_dev, st)) return rc;
   // agts = relu(GN(linear(agts)) + res)                                                              :707-709
   LinearArgs l = with_w(agt_rows(A0, nullptr, w.lw, w.lg, w.lb, agts_in, kLin, agts_out), 7);
   return lgcn_launch_linear(l, st);

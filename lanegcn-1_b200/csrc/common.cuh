@@ -174,6 +174,10 @@ struct LinearArgs {
   // optional caller-provided scratch for that split (lgcn_linear128_workspace_bytes); without it the tcgen05 path uses
   // the library's lazily allocated per-device scratch ring (lgcn_linear128 only)
   void* split_ws;
+  // optional (tcgen05, one output block): a SECOND Linear chained inside the kernel, y = epi2(W2 . epi1(...)): its tf32
+  // images are the block that follows the sources' blocks in w_hi / w_lo; flags2 = its LGCN_EPI_* (no GroupNorm)
+  int chain;
+  int flags2;
 };
 int lgcn_debug_get();
 int lgcn_launch_linear_simt(const LinearArgs& a, cudaStream_t st);

@@ -115,6 +115,7 @@ struct FusedArgs {
   const int32_t* m_dev;  // ... and, when not NULL, the live row count in device memory (min(*m_dev, M) rows are processed)
   int n_keys;
   int chain;             // 1: ctr2 + GN + residual + ReLU inside the kernel
+  int flags2;            // linear mode with LCHAIN: LGCN_EPI_* of the second Linear (no GN)
   // linear mode (tab == nullptr): out = epilogue( sum_k W_k . src[k][ idx[k] ? idx[k][row] : row ] ), the generic
   // bias-free Linear (+GroupNorm, +ReLU, +residual, +ReLU) of lgcn_linear128 with up to three K=128 sources
   const float* src[3];
@@ -132,7 +133,9 @@ struct FusedArgs {
 // LINEAR = false: one LaneConv block (plan / table driven);  LINEAR = true: the generic Linear of lgcn_linear128.
 // Two instantiations so that neither hot loop carries the other mode's branches and registers.
 // KS4 (linear mode only): rank-4 update of the accumulators by four extra input columns (A2M.meta, lanegcn.py:387-395).
-template <bool LINEAR, bool KS4 = false>
+// LCHAIN (linear mode only): a second Linear (weights = the block after the sources' blocks) is applied to the first one's
+// result without leaving the kernel, like ctr2: y = epi2(W2 . epi1(sum_s W_s x_s))  (Att: ctx.0 -> ctx.1, lanegcn.py:698-700).
+template <bool LINEAR, bool KS4 = false, bool LCHAIN = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                  const __grid_constant__ CUtensorMap whi_map, const __grid_constant__ CUtensorMap wlo_map) {
@@ -199,7 +202,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const int64_t lin_ldw = a.ldw;
   const int lin_flags = a.flags;
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
-  const bool chain = a.chain != 0;
+  const bool chain = LINEAR ? LCHAIN : a.chain != 0;
+  const int lin_flags2 = a.flags2;
   const int dbg = a.dbg;
 #ifdef LGCN_TIMELINE
   long long* tl = (blockIdx.x == 0 && (dbg & 256)) ? a.tl : nullptr;
@@ -652,7 +656,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
     // linear mode: the generic Linear epilogue [GroupNorm] [ReLU] [+ residual] [ReLU], deferred like finish_tile
     auto finish_linear = [&](int64_t pm0) {
       const int64_t m = pm0 + r;
-      const bool live = m < M && (lin_flags & LGCN_EPI_RES);
+      const int fl = LCHAIN ? lin_flags2 : lin_flags;   // with a chain this is the SECOND Linear's epilogue
+      const bool live = m < M && (fl & LGCN_EPI_RES);
       const float4* resp = reinterpret_cast<const float4*>(lin_res + (live ? m : 0) * LGCN_C + h * 64);
       float4 ra[8], rb[8];
 #pragma unroll
@@ -671,8 +676,8 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           }
         }
       }
-      if (lin_flags & LGCN_EPI_GN) gn(gam);
-      if (lin_flags & LGCN_EPI_RELU1) {
+      if (!LCHAIN && (fl & LGCN_EPI_GN)) gn(gam);
+      if (fl & LGCN_EPI_RELU1) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
       }
@@ -687,7 +692,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         f[34 + 4 * c] += rb[c].z;
         f[35 + 4 * c] += rb[c].w;
       }
-      if (lin_flags & LGCN_EPI_RELU2) {
+      if (fl & LGCN_EPI_RELU2) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
       }
@@ -763,15 +768,17 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         for (int i = 0; i < 4; ++i) vr[i] = vrn[i];
         kseq = (kseq + 1) & 3;
       }
-      if (linear) {   // the epilogue runs three stages into the next tile (finish_linear below)
+      if (linear && !LCHAIN) {   // the epilogue runs three stages into the next tile (finish_linear below)
         pending = true;
         pending_m0 = m0;
         continue;
       }
       drain(true);
-      gn(gam);
+      if (!linear || (lin_flags & LGCN_EPI_GN)) gn(gam);
+      if (!linear || (lin_flags & LGCN_EPI_RELU1)) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+        for (int c = 0; c < 64; ++c) f[c] = fmaxf(f[c], 0.f);
+      }
       if (!chain) {
         store_out(m0);
         continue;
@@ -1086,6 +1093,7 @@ int set_fused_attrs() {
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   return 0;
 }
 }  // namespace
@@ -1112,6 +1120,9 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   if (la.m <= 0) return 0;
   LGCN_CHECK_ARG(la.n_out_blocks == 1 && (la.ks == 0 || la.ks == 4) && la.n_src >= 1 && la.n_src <= 3,
                  "linear_fused: unsupported shape");
+  LGCN_CHECK_ARG(!la.chain || (la.ks == 0 && la.w_hi && la.w_lo && !(la.flags2 & LGCN_EPI_GN) &&
+                               !(la.flags & (LGCN_EPI_RES | LGCN_EPI_RELU2))),
+                 "linear_fused: a chained second Linear needs pre-split weights, no GroupNorm of its own and no residual on the first");
   if (int rc = set_fused_attrs()) return rc;
   const float *w_hi = la.w_hi, *w_lo = la.w_lo;
   int slot = -1;
@@ -1147,8 +1158,8 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   }
   CUtensorMap map, mhi, mlo;
   if (int rc = make_out_map(&map, la.out, LGCN_C, la.m, la.ldo)) return rc;
-  if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)la.n_src * LGCN_C, LGCN_C, 32, 128)) return rc;
-  if (int rc = make_cross_map(&mlo, w_lo, (int64_t)la.n_src * LGCN_C)) return rc;
+  if (int rc = make_map_2d(&mhi, w_hi, LGCN_C, (int64_t)(la.n_src + (la.chain ? 1 : 0)) * LGCN_C, LGCN_C, 32, 128)) return rc;
+  if (int rc = make_cross_map(&mlo, w_lo, (int64_t)(la.n_src + (la.chain ? 1 : 0)) * LGCN_C)) return rc;
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   for (int k = 0; k < la.n_src; ++k) {
@@ -1164,10 +1175,11 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
     a.wx = la.W + (int64_t)la.n_src * LGCN_C;
     a.ldw = (int64_t)la.n_src * LGCN_C + 4;
   }
-  a.flags = la.flags; a.M = la.m; a.m_dev = la.m_dev; a.n_keys = la.n_src - 1; a.chain = 0; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
+  a.flags = la.flags; a.M = la.m; a.m_dev = la.m_dev; a.n_keys = la.n_src - 1; a.chain = la.chain ? 1 : 0; a.flags2 = la.flags2; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
   const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  if (la.ks == 4) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
+  if (la.chain) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
+  else if (la.ks == 4) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   else LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   LGCN_LAUNCH_OK();
   if (slot >= 0) {
