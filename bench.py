@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-reference", action="store_true")
+    ap.add_argument("--debug-flags", type=int, default=0,
+                    help="A/B switches of include/lgcn_debug.h that keep results right (e.g. 16384 no PDL, 65536 / 131072 unfused Att pieces)")
     return ap.parse_args()
 
 
@@ -341,6 +343,8 @@ def run_forward(args):
         if world > 1:
             dist.barrier()
     lib = _C.lib()
+    if args.debug_flags:
+        lib.lgcn_debug_flags(args.debug_flags)
 
     # ---- workload: global batch, this rank's contiguous shard
     cfg = args.config

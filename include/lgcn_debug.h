@@ -22,7 +22,8 @@ extern "C" {
  * not on the stress case of tools/precision_fused.py); 32768 = one-block Linears on the first-generation k_linear_tc
  * instead of the linear mode of the aggregate-first kernel (results stay right); 16384 = launch the tcgen05 kernels without
  * the programmatic-dependent-launch attribute (results stay right); 65536 = Att: ctx.1 as its own launch instead of chained
- * inside ctx.0's kernel (results stay right). */
+ * inside ctx.0's kernel (results stay right); 131072 = the K=2 heads (MapNet input / seg, Att dist) as their own launches
+ * instead of computed inside the following Linear's kernel (results stay right). */
 int lgcn_debug_flags(int flags);
 /* Profiling aid: device buffer [1024][8] of int64 clock stamps filled by CTA 0 of the aggregate-first LaneConv kernel
  * while debug flag 256 is set (tools/timeline_fused.py). */

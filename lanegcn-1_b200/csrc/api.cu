@@ -415,8 +415,16 @@ int lgcn_att_layer(const float* agts_in, float* agts_out, const float* ctx, cons
   LinearArgs ag = with_w(agt_rows(agts_in, nullptr, w.aw, nullptr, nullptr, nullptr, 0, A1), 6);
   if (int rc = lgcn_launch_linear(ag, fk->on(1, st))) return rc;
   // dist = relu(GN(L(relu(L2(agt_ctrs[hi] - ctx_ctrs[wi])))))                      lanegcn.py:693-694
-  if (int rc = lgcn_launch_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, n_pairs_dev, st)) return rc;
+  // (with pre-split weights the K=2 head is computed inside dist.2's kernel: its rows never exist in memory)
+  const bool head_in = pre && !(lgcn_debug_get() & 131072);
+  if (!head_in)
+    if (int rc = lgcn_launch_mlp2_in(agt_ctrs, hi, ctx_ctrs, wi, w.d0w, w.d0b, P0, n_pairs, n_pairs_dev, st)) return rc;
   LinearArgs d2 = with_w(pair_rows(P0, nullptr, w.d2w, w.d2g, w.d2b, nullptr, LGCN_EPI_GN | LGCN_EPI_RELU1, P1), 0);
+  if (head_in) {
+    d2.head_w = w.d0w;   // d0w [128][2] | d0b [128] are adjacent in the pack
+    d2.head_p = agt_ctrs; d2.head_ip = hi;
+    d2.head_q = ctx_ctrs; d2.head_iq = wi;
+  }
   if (int rc = lgcn_launch_linear(d2, st)) return rc;
   if (fk->join(0, st)) return -2;
   // ctx = L(relu(GN(L384(cat(dist, query, ctx[wi])))))  — split-K over the three sources, no cat   :698-700

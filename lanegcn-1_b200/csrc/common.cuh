@@ -178,6 +178,13 @@ struct LinearArgs {
   // images are the block that follows the sources' blocks in w_hi / w_lo; flags2 = its LGCN_EPI_* (no GroupNorm)
   int chain;
   int flags2;
+  // optional (tcgen05, pre-split weights): source 0 is COMPUTED instead of read, relu(W1 . (p[ip ? ip[m] : m] - q[iq ? iq[m] : m]) + b1)
+  // with head_w = W1 [128][2] | b1 [128] (the nn.Linear(2, 128) + ReLU heads; q may be NULL); a[0] / idx[0] are ignored
+  const float* head_w;
+  const float* head_p;
+  const int32_t* head_ip;
+  const float* head_q;
+  const int32_t* head_iq;
 };
 int lgcn_debug_get();
 int lgcn_launch_linear_simt(const LinearArgs& a, cudaStream_t st);

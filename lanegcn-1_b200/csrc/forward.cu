@@ -274,11 +274,17 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
     const float* src[2] = {a.node_ctrs, a.node_feats};
     for (int i = 0; i < 2; ++i) {
       const float* w = mlp[i];   // W1[128,2] | b1[128] | W2[128,128] | gamma | beta
-      if (int rc = lgcn_launch_mlp2_in(src[i], nullptr, nullptr, nullptr, w, w + 2 * LGCN_C, hid, N, n_nodes, st)) return rc;
+      const bool head_in = !(lgcn_debug_get() & 131072);   // the K=2 head computed inside the Linear's kernel
+      if (!head_in)
+        if (int rc = lgcn_launch_mlp2_in(src[i], nullptr, nullptr, nullptr, w, w + 2 * LGCN_C, hid, N, n_nodes, st)) return rc;
       LinearArgs l = lgcn_lin1(hid, nullptr, w + 3 * LGCN_C, w + 3 * LGCN_C + CC, w + 4 * LGCN_C + CC, i ? t0 : nullptr,
                                i ? (LGCN_EPI_GN | LGCN_EPI_RES | LGCN_EPI_RELU2) : LGCN_EPI_GN, i ? a.nodes : t0, N, n_nodes);
       l.w_hi = prep + (i ? P.seg_hi : P.in_hi);
       l.w_lo = prep + (i ? P.seg_lo : P.in_lo);
+      if (head_in) {
+        l.head_w = w;   // W1 [128][2] | b1 [128]
+        l.head_p = src[i];
+      }
       if (int rc = lgcn_launch_linear(l, st)) return rc;
     }
     if (int rc = lgcn_laneconv_stack_presplit(a.nodes, t0, xa, plan, L.E_cap, L.n_keys, 4, a.w.map_fuse, prep + P.map_hi,

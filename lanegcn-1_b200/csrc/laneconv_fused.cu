@@ -64,7 +64,9 @@ constexpr int kSmemGam = kSmemOut + 8 * 4096;                // gamma1 | beta1 |
 constexpr int kSmemStat = kSmemGam + 4 * 512;                // float2 [2][128]
 constexpr int kSmemTab = kSmemStat + 2 * 128 * 8;            // int32 [4][256]: table entries in flight (cp.async)
 constexpr int kSmemBar = kSmemTab + 4 * 256 * 4;
-constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kSmemHead = kSmemBar + 256;                    // 2 KB: float4 [128] = (w0, w1, b, 0) of a K=2 head (MLP0), or the
+                                                             //       [128][4] weights of the 4 extra columns (KS4)
+constexpr int kSmemTotal = kSmemHead + 2048;
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 1;
 constexpr uint32_t kIdesc = idesc_tf32(128, 128);
@@ -126,6 +128,13 @@ struct FusedArgs {
   const float* wx;       // ... and their weights: wx[n * ldw + j] = W[n, n_src*128 + j]
   int64_t ldw;
   int flags;             // LGCN_EPI_* (linear mode)
+  // MLP0: source 0 is not read but COMPUTED per row: relu(W1 . (p[ip ? ip[m] : m] - q[iq ? iq[m] : m]) + b1), the
+  // nn.Linear(2, 128) + ReLU heads in front of MapNet.input / seg and Att.dist (lanegcn.py:277-286, 644-648, 693)
+  const float* head_w;   // W1 [128][2] | b1 [128]
+  const float2* head_p;
+  const int32_t* head_ip;
+  const float2* head_q;  // may be NULL (no subtraction)
+  const int32_t* head_iq;
   long long* tl;         // timeline buffer [1024][8] (dbg & 256, CTA 0 only)
   int dbg;               // lgcn_debug_flags (ablation: 1 no stores, 4 no MMAs, 8 no loads, 32 no A conversion, 64 no flushes, 128 no weight loads)
 };
@@ -135,7 +144,7 @@ struct FusedArgs {
 // KS4 (linear mode only): rank-4 update of the accumulators by four extra input columns (A2M.meta, lanegcn.py:387-395).
 // LCHAIN (linear mode only): a second Linear (weights = the block after the sources' blocks) is applied to the first one's
 // result without leaving the kernel, like ctr2: y = epi2(W2 . epi1(sum_s W_s x_s))  (Att: ctx.0 -> ctx.1, lanegcn.py:698-700).
-template <bool LINEAR, bool KS4 = false, bool LCHAIN = false>
+template <bool LINEAR, bool KS4 = false, bool LCHAIN = false, bool MLP0 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
                  const __grid_constant__ CUtensorMap whi_map, const __grid_constant__ CUtensorMap wlo_map) {
@@ -172,6 +181,17 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       g[threadIdx.x] = threadIdx.x < 128 ? a.gn[threadIdx.x] : a.beta[threadIdx.x - 128];
     }
   }
+  if constexpr (MLP0) {   // (w0, w1, b, 0) per output channel: one broadcast 16-byte shared load per computed value
+    if (threadIdx.x < 128) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(a.head_w) + threadIdx.x);
+      reinterpret_cast<float4*>(smem + kSmemHead)[threadIdx.x] = make_float4(w.x, w.y, __ldg(a.head_w + 256 + threadIdx.x), 0.f);
+    }
+  }
+  if constexpr (KS4) {    // the [128][4] weights of the extra columns (64 strided global loads per row otherwise)
+    if (threadIdx.x < 128)
+      reinterpret_cast<float4*>(smem + kSmemHead)[threadIdx.x] =
+          __ldg(reinterpret_cast<const float4*>(a.wx + (int64_t)threadIdx.x * a.ldw));
+  }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(tmem_slot)),
@@ -182,7 +202,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  lgcn_pdl_wait();   // everything above touched only this CTA's shared / tensor memory and the (static) norm vectors
+  lgcn_pdl_wait();   // everything above touched only this CTA's shared / tensor memory and the (static) weights
 
   // scalars only below (a by-value struct captured by reference in a lambda ends up in local memory)
   const int64_t M = lgcn_devn(a.m_dev, a.M);
@@ -198,8 +218,6 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
   const int32_t* __restrict__ idx2 = a.idx[2];
   const float* __restrict__ lin_res = a.res;
   const float* __restrict__ lin_xs = a.xs;
-  const float* __restrict__ lin_wx = a.wx;
-  const int64_t lin_ldw = a.ldw;
   const int lin_flags = a.flags;
   const int n_keys = a.n_keys, nk = a.n_keys + 1;
   const bool chain = LINEAR ? LCHAIN : a.chain != 0;
@@ -403,6 +421,7 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
         const bool own = linear ? key_idx(kk) == nullptr : kk == 0;
         v = self_src(t);
         if (!own && v >= 0) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot0 + 1024u * ring) : "memory");
+        if (MLP0 && kk == 0) v = -1;   // computed source: the ring slot is only zero-filled
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) vr[i] = __shfl_sync(0xffffffffu, v, 8 * i + (lane >> 2));
@@ -668,10 +687,10 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       if constexpr (KS4) {   // the weights of the 4 extra columns are broadcast loads from L2
         if (m < M) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(lin_xs + m * 4));
-          const float* wr = lin_wx + (int64_t)(h * 64) * lin_ldw;
+          const uint32_t wr = sbase + kSmemHead + (h * 64) * 16;
 #pragma unroll
           for (int c = 0; c < 64; ++c) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wr + (int64_t)c * lin_ldw));
+            const float4 w = ld_shared_f4(wr + c * 16);
             f[c] = fmaf(x.w, w.w, fmaf(x.z, w.z, fmaf(x.y, w.y, fmaf(x.x, w.x, f[c]))));
           }
         }
@@ -698,10 +717,32 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
       }
       store_out(pm0);
     };
+    // MLP0: this row's input of the K=2 head, read a tile ahead (two dependent loads: index, then centre)
+    const float2* __restrict__ head_p = a.head_p;
+    const float2* __restrict__ head_q = a.head_q;
+    const int32_t* __restrict__ head_ip = a.head_ip;
+    const int32_t* __restrict__ head_iq = a.head_iq;
+    auto head_xy = [&](int64_t t) -> float2 {
+      const int64_t m = t * kTileM + r;
+      float2 x = make_float2(0.f, 0.f);
+      if (MLP0 && t < n_tiles && m < M) {
+        x = __ldg(head_p + (head_ip ? __ldg(head_ip + m) : m));
+        if (head_q) {
+          const float2 y = __ldg(head_q + (head_iq ? __ldg(head_iq + m) : m));
+          x.x -= y.x;
+          x.y -= y.y;
+        }
+      }
+      return x;
+    };
+    float2 xy_next = head_xy(blockIdx.x);
     bool pending = false;
     int64_t pending_m0 = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += grid) {
       const int64_t m0 = t * kTileM;
+      const float2 xy = xy_next;
+      const bool head_live = m0 + r < M;
+      if (MLP0) xy_next = head_xy(t + grid);
       if (!pending) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) f[c] = 0.f;
@@ -726,6 +767,17 @@ k_laneconv_fused(const FusedArgs a, const __grid_constant__ CUtensorMap out_map,
           stage_peek();
           LGCN_TK(1);
           take(cur, xs);
+          if (MLP0 && kk == 0) {   // source 0 = relu(W1 . xy + b1): same association as addmm(bias, x, W^T) in fp32 (k_mlp2_in)
+            const uint32_t wq = sbase + kSmemHead + (32 * kc + 16 * h) * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 w0 = ld_shared_f4(wq + (4 * c) * 16), w1 = ld_shared_f4(wq + (4 * c + 1) * 16),
+                           w2 = ld_shared_f4(wq + (4 * c + 2) * 16), w3 = ld_shared_f4(wq + (4 * c + 3) * 16);
+              cur[c] = make_float4(fmaxf(fmaf(xy.y, w0.y, xy.x * w0.x) + w0.z, 0.f), fmaxf(fmaf(xy.y, w1.y, xy.x * w1.x) + w1.z, 0.f),
+                                   fmaxf(fmaf(xy.y, w2.y, xy.x * w2.x) + w2.z, 0.f), fmaxf(fmaf(xy.y, w3.y, xy.x * w3.x) + w3.z, 0.f));
+              if (!head_live) cur[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
           LGCN_TL_PROD(4);
           stage_begin_peeked();
           LGCN_TK(4);
@@ -1094,6 +1146,7 @@ int set_fused_attrs() {
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+  LGCN_CUDA_OK(cudaFuncSetAttribute(k_laneconv_fused<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   return 0;
 }
 }  // namespace
@@ -1120,6 +1173,8 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   if (la.m <= 0) return 0;
   LGCN_CHECK_ARG(la.n_out_blocks == 1 && (la.ks == 0 || la.ks == 4) && la.n_src >= 1 && la.n_src <= 3,
                  "linear_fused: unsupported shape");
+  LGCN_CHECK_ARG(!la.head_w || (la.ks == 0 && !la.chain && la.w_hi && la.w_lo && la.head_p),
+                 "linear_fused: a computed first source needs pre-split weights and excludes ks / chain");
   LGCN_CHECK_ARG(!la.chain || (la.ks == 0 && la.w_hi && la.w_lo && !(la.flags2 & LGCN_EPI_GN) &&
                                !(la.flags & (LGCN_EPI_RES | LGCN_EPI_RELU2))),
                  "linear_fused: a chained second Linear needs pre-split weights, no GroupNorm of its own and no residual on the first");
@@ -1166,10 +1221,16 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
     a.src[k] = la.a[k];
     a.idx[k] = la.idx[k];
   }
-  a.X = la.a[0]; a.XA = la.a[0]; a.tab = nullptr;
+  if (la.head_w) {   // source 0 is computed in the kernel: nothing is read through src[0] (any valid address will do)
+    a.src[0] = la.out;
+    a.idx[0] = nullptr;
+    a.head_w = la.head_w; a.head_p = (const float2*)la.head_p; a.head_ip = la.head_ip;
+    a.head_q = (const float2*)la.head_q; a.head_iq = la.head_iq;
+  }
+  a.X = a.src[0]; a.XA = a.src[0]; a.tab = nullptr;
   a.gn = (la.flags & LGCN_EPI_GN) ? la.gamma : nullptr;
   a.beta = la.beta;
-  a.res = la.res ? la.res : la.a[0];
+  a.res = la.res ? la.res : a.src[0];
   if (la.ks == 4) {
     a.xs = la.xs;
     a.wx = la.W + (int64_t)la.n_src * LGCN_C;
@@ -1178,7 +1239,8 @@ int lgcn_launch_linear_fused(const LinearArgs& la, cudaStream_t st) {
   a.flags = la.flags; a.M = la.m; a.m_dev = la.m_dev; a.n_keys = la.n_src - 1; a.chain = la.chain ? 1 : 0; a.flags2 = la.flags2; a.dbg = lgcn_debug_get(); a.tl = g_timeline;
   const int64_t n_tiles = (la.m + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < num_sms() ? n_tiles : num_sms());
-  if (la.chain) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
+  if (la.head_w) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false, false, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
+  else if (la.chain) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   else if (la.ks == 4) LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, true>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   else LGCN_CUDA_OK(lgcn_launch_pdl(k_laneconv_fused<true, false>, grid, kNumThreads, kSmemTotal, st, a, map, mhi, mlo));
   LGCN_LAUNCH_OK();
