@@ -240,9 +240,8 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
     if (int rc = lgcn_zero_async(a.status, 8 * sizeof(int32_t), st)) return rc;
     // the three pair lists depend on the centres only (lanegcn.py:672-689; both Att layers of a block share theirs) and
     // not on the edge lists: with an auxiliary stream they are built beside the CSR / plan chain
-    if (fk.fork(0, st)) return -2;
+    if (fk.fork(0, st) || fk.fork(1, st)) return -2;
     {
-      cudaStream_t ps = fk.on(0, st);
       const float* agt_c[3] = {a.node_ctrs, a.actor_ctrs, a.actor_ctrs};
       const float* ctx_c[3] = {a.actor_ctrs, a.node_ctrs, a.actor_ctrs};
       const int32_t* agt_o[3] = {a.node_off, a.actor_off, a.actor_off};
@@ -250,12 +249,14 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
       const int64_t n_agt[3] = {N, A, A};
       const int32_t* n_agt_dev[3] = {n_nodes, n_actors, n_actors};
       const int64_t n_ctx[3] = {A, N, A};
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i) {   // the A2M list on the first branch, M2A and A2A on the second
+        cudaStream_t ps = fk.on(i == 0 ? 0 : 1, st);
         if (int rc = lgcn_launch_pairs(agt_c[i], ctx_c[i], agt_o[i], ctx_o[i], a.cap_scenes, n_agt[i], n_agt_dev[i],
                                        a.dist_th[i], a.keep_pair_quirk, (int32_t*)(ws + L.p_rowptr[i]), ws + L.p_ws[i],
                                        a.cap_pairs[i], (int32_t*)(ws + L.p_hi[i]), (int32_t*)(ws + L.p_wi[i]), p_tot + i,
                                        a.status, a.status + 1 + i, LGCN_ST_OVERFLOW_A2M << i, LGCN_ST_EMPTY_A2M << i, n_ctx[i], ps))
           return rc;
+      }
     }
     // utils.to_long + the offset / cat loops of graph_gather (lanegcn.py:191-208)
     if (int rc = lgcn_offset_indices(a.local_idx, a.idx_bytes, a.segs, a.segs + n_seg + 1, n_seg, a.cap_index, e64, stream))
@@ -265,7 +266,7 @@ extern "C" int lgcn_forward(const LgcnForwardArgs* args, void* stream) {
                                            ws + L.csr_ws, a.status + 4, st))
       return rc;
     if (int rc = lgcn_launch_plan_build(rowptr, col, L.n_keys, N, n_nodes, L.E_cap, plan, st)) return rc;
-    if (fk.join(0, st)) return -2;
+    if (fk.join(0, st) || fk.join(1, st)) return -2;
   }
 
   if (a.stages & LGCN_STAGE_MAPNET) {
