@@ -37,7 +37,10 @@ template <int RT, int KIN>
 __device__ __forceinline__ void rows_fma(const float* __restrict__ in, int ld, const float* __restrict__ Wt, int nout,
                                          int co0, float (&acc)[RT][4]) {
   if (co0 >= nout) return;
-#pragma unroll 2
+  // weight rows come straight from L2 (each warp streams its own matrices): the unroll factor is the number of 4-row
+  // batches in flight, and with few rows per warp the loop is a chain of L2 round trips (94 us for 320 actors at 2)
+  constexpr int kUnroll = RT <= 4 ? 8 : 4;
+#pragma unroll kUnroll
   for (int k = 0; k < KIN; k += 4) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)k * nout + co0));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wt + (int64_t)(k + 1) * nout + co0));
@@ -298,18 +301,20 @@ extern "C" int lgcn_pred_net(const float* actors, const float* actor_ctrs, const
   LGCN_CUDA_OK(cudaGetDevice(&dev));
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   if (dev >= 0 && dev < 64 && g_attr[dev].exchange(1) == 0) {
+    LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::floats * 4));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::floats * 4));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<6>::floats * 4));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<8>::floats * 4));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<10>::floats * 4));
     LGCN_CUDA_OK(cudaFuncSetAttribute(k_pred_net<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<12>::floats * 4));
   }
-  // actors per CTA (2 RT): a warp's serial work grows with RT and the CTAs run one per SM in waves, so pick the group
-  // size with the smallest waves x RT (for 2,560 actors on 148 SMs: 20 actors per CTA = 128 CTAs = one wave)
-  int best = 4;
+  // actors per CTA (2 RT): the CTAs run one per SM in waves and a CTA takes about 15 us + 15 us x RT (measured: 45 / 78 /
+  // 166 us at RT = 2 / 4 / 10), so pick the group size with the smallest waves x (RT + 1)
+  // (2,560 actors on 148 SMs: 20 per CTA = 128 CTAs = one wave; 320 actors: 4 per CTA = 80 CTAs)
+  int best = 2;
   int64_t best_cost = -1;
-  for (int rt : {4, 6, 8, 10, 12}) {
-    const int64_t ctas = (n_actors + 2 * rt - 1) / (2 * rt), cost = ((ctas + sms - 1) / sms) * rt;
+  for (int rt : {2, 4, 6, 8, 10, 12}) {
+    const int64_t ctas = (n_actors + 2 * rt - 1) / (2 * rt), cost = ((ctas + sms - 1) / sms) * (rt + 1);
     if (best_cost < 0 || cost < best_cost) {
       best = rt;
       best_cost = cost;
@@ -321,6 +326,7 @@ extern "C" int lgcn_pred_net(const float* actors, const float* actor_ctrs, const
   k_pred_net<RT_><<<grid, kThreads, Smem<RT_>::floats * 4, st>>>(actors, actor_ctrs, actor_off, n_scenes, rot, orig, wpack, \
                                                                  cls, reg, n_actors, n_actors_dev)
   switch (best) {
+    case 2: LGCN_PRED(2); break;
     case 4: LGCN_PRED(4); break;
     case 6: LGCN_PRED(6); break;
     case 8: LGCN_PRED(8); break;
